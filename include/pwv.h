@@ -1,0 +1,128 @@
+/*
+ * pwv.h -- C-ABI of the B200-native IAF-vocoder generation path.
+ *
+ * The reference (andabi/parallel-wavenet-vocoder @ 6c2fa069) has no FFI: its boundary for this
+ * path is Python-level -- `IAFVocoder(batch_size, length)(wav, melspec, is_training)` building a
+ * TF graph (reference models.py:18-78) that one `sess.run` executes (reference generate.py:68).
+ * This header is what a binding for that path would bind instead of the TF session:
+ *
+ *   reference interface (file:line)                         replaced by
+ *   ------------------------------------------------------  --------------------------------------
+ *   hp.model.* / hp.signal.* read at graph build             pwv_hparams + pwv_model_create
+ *     (models.py:20,26-70,106-133)
+ *   tf.get_variable(name, shape) per variable                pwv_model_load_weight (same names, same
+ *     (modules.py:152-164,179,210-248; models.py:128)          [k,Cin,Cout] layouts)
+ *   tf.train.Saver(...).restore / global_variables_init      pwv_model_finalize (packs + uploads)
+ *     (generate.py:55-66)
+ *   sess.run(pred_wav_op)  (generate.py:68) ==               pwv_forward (device buffers, async) /
+ *     IAFVocoder.__call__ (models.py:23-78) ->                 pwv_forward_host (host buffers, sync)
+ *     LinearIAFLayer (modules.py:53-60) ->
+ *     WaveNet.__call__ (modules.py:129-166) ->
+ *     causal_conv (modules.py:11-43)
+ *   Logistic(0,1).sample in-graph (models.py:32-33)          the caller passes `noise` explicitly
+ *
+ * Conventions: plain C, no C++/torch types. Every function returns 0 on success or a negative
+ * PWV_E* code and never throws, exits or prints; pwv_last_error() returns a thread-local message
+ * for the last failure on the calling thread. Buffers are contiguous row-major float32:
+ * noise/wav [N][T], mel [N][1+T/hop][n_mels]. The library owns only the packed weights; the caller
+ * owns inputs, outputs and workspace. pwv_forward enqueues on `stream` and returns without
+ * synchronising; it allocates nothing. One model may be used from several host threads as long as
+ * each uses its own workspace and stream. There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with PWV_ECUDA.
+ */
+#ifndef PWV_H_
+#define PWV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWV_VERSION 100          /* major*10000 + minor*100 + patch */
+#define PWV_MAX_FLOWS 8
+#define PWV_MAX_LAYERS 64
+
+/* error codes */
+#define PWV_OK 0
+#define PWV_EINVAL (-1)          /* bad argument / unsupported hyper-parameter                  */
+#define PWV_ESTATE (-2)          /* call sequence (e.g. forward before finalize)                */
+#define PWV_ECUDA (-3)           /* CUDA runtime / driver error (message has the CUDA string)   */
+#define PWV_ENOMEM (-4)          /* workspace too small / allocation failed                     */
+#define PWV_ENAME (-5)           /* unknown variable name or wrong shape in load_weight         */
+
+/* arithmetic of the gated-layer contractions */
+#define PWV_PREC_FP32 0          /* fp32 FFMA on CUDA cores; bit-for-bit IEEE fp32 accumulate    */
+#define PWV_PREC_TF32X3 1        /* tcgen05 kind::tf32, 3-term split (fp32-level parity)         */
+#define PWV_PREC_BF16 2          /* tcgen05 kind::f16 bf16 operands, fp32 accumulate            */
+
+typedef struct pwv_model pwv_model;   /* opaque */
+typedef void* pwv_stream;             /* a cudaStream_t / CUstream (0 = legacy default stream) */
+
+/* POD mirror of the hparams the path reads (reference hparams/default.yaml:11-33). */
+typedef struct pwv_hparams {
+  int32_t n_iaf;                  /* model.n_iaf                                              */
+  int32_t filter_width;           /* model.filter_width; only 2 is implemented                 */
+  int32_t residual_channels;      /* model.residual_channels (R)                               */
+  int32_t dilation_channels;      /* model.dilation_channels (D); must equal R                 */
+  int32_t skip_channels;          /* model.skip_channels (S); must equal 2*R                   */
+  int32_t condition_channels;     /* model.condition_channels (Cc)                             */
+  int32_t n_mels;                 /* signal.n_mels                                             */
+  int32_t hop_length;             /* signal.hop_length                                         */
+  int32_t use_biases;             /* model.use_biases                                          */
+  int32_t use_skip_connection;    /* model.use_skip_connection; only 0 is implemented          */
+  int32_t precision;              /* PWV_PREC_*                                                */
+  int32_t n_layers[PWV_MAX_FLOWS];                     /* len(model.dilations[i])              */
+  int32_t dilations[PWV_MAX_FLOWS][PWV_MAX_LAYERS];    /* model.dilations[i][j]                */
+} pwv_hparams;
+
+/* Optional debug taps for parity tests (all device pointers, any may be NULL). */
+typedef struct pwv_taps {
+  float* flow_out;                /* [n_iaf][N][T]: x after each flow (reference models.py:67)  */
+  int32_t layer_flow, layer_body, layer_index;  /* which gated layer to capture ...            */
+  float* layer_out;               /* ... [N][T][R]: its dense_output (reference modules.py:251) */
+  float* scale_shift;             /* [n_iaf][2][N][T]: WaveNet outputs (reference modules.py:56-57) */
+} pwv_taps;
+
+int pwv_version(void);
+const char* pwv_last_error(void);
+/* Number of CUDA devices visible, or a negative PWV_ECUDA. */
+int pwv_device_count(void);
+
+/* Validate hparams and create an empty model on the current CUDA device. */
+int pwv_model_create(const pwv_hparams* hp, pwv_model** out);
+int pwv_model_destroy(pwv_model* m);
+
+/* Number of variables the model expects, and the i-th one's TF name / shape (ndim <= 3). */
+int pwv_model_num_variables(const pwv_model* m);
+int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[3], int* ndim);
+
+/* Copy one variable (HOST pointer, float32, TF layout) into the model's staging area. */
+int pwv_model_load_weight(pwv_model* m, const char* tf_name, const float* host_data,
+                          const int64_t* shape, int ndim);
+/* Check that every variable was loaded, repack into the kernels' device layouts, upload. */
+int pwv_model_finalize(pwv_model* m);
+
+/* Bytes of device workspace pwv_forward needs for a batch of N utterances of T samples. */
+int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes);
+
+/* noise [N][T], mel [N][1+T/hop][n_mels] -> wav [N][T]; all DEVICE pointers; T % hop == 0.
+ * Asynchronous on `stream`. `taps` may be NULL. */
+int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav,
+                void* workspace, size_t workspace_bytes, int N, int T,
+                pwv_stream stream, const pwv_taps* taps);
+
+/* Same computation with HOST buffers (pinned or pageable): H2D copies, pwv_forward, D2H copy and
+ * a stream synchronise inside the call. Device staging is cached inside the model and grown on
+ * demand (the only entry point that allocates). */
+int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* wav,
+                     int N, int T, pwv_stream stream);
+
+/* Kernel launches enqueued by the most recent pwv_forward on this model (for bench accounting). */
+int pwv_last_launch_count(const pwv_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PWV_H_ */

@@ -1,0 +1,117 @@
+"""ctypes binding of the C-ABI in include/pwv.h (libpwv_b200.so, built in-tree by
+`__graft_entry__.build()` / `csrc/Makefile`).
+
+There is deliberately no fallback: if the library is missing or fails to load, importing the
+product path raises, and every compute entry point fails without a CUDA device.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpwv_b200.so')
+
+PWV_MAX_FLOWS = 8
+PWV_MAX_LAYERS = 64
+PREC = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
+
+EXPORTS = (
+    'pwv_version', 'pwv_last_error', 'pwv_device_count', 'pwv_model_create', 'pwv_model_destroy',
+    'pwv_model_num_variables', 'pwv_model_variable', 'pwv_model_load_weight', 'pwv_model_finalize',
+    'pwv_workspace_bytes', 'pwv_forward', 'pwv_forward_host', 'pwv_last_launch_count',
+)
+
+
+class PwvHparams(ctypes.Structure):
+    _fields_ = [
+        ('n_iaf', ctypes.c_int32), ('filter_width', ctypes.c_int32),
+        ('residual_channels', ctypes.c_int32), ('dilation_channels', ctypes.c_int32),
+        ('skip_channels', ctypes.c_int32), ('condition_channels', ctypes.c_int32),
+        ('n_mels', ctypes.c_int32), ('hop_length', ctypes.c_int32),
+        ('use_biases', ctypes.c_int32), ('use_skip_connection', ctypes.c_int32),
+        ('precision', ctypes.c_int32),
+        ('n_layers', ctypes.c_int32 * PWV_MAX_FLOWS),
+        ('dilations', (ctypes.c_int32 * PWV_MAX_LAYERS) * PWV_MAX_FLOWS),
+    ]
+
+
+class PwvTaps(ctypes.Structure):
+    _fields_ = [
+        ('flow_out', ctypes.c_void_p),
+        ('layer_flow', ctypes.c_int32), ('layer_body', ctypes.c_int32), ('layer_index', ctypes.c_int32),
+        ('layer_out', ctypes.c_void_p),
+        ('scale_shift', ctypes.c_void_p),
+    ]
+
+
+class PwvError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'pwv error {code}: {message}')
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'(or `make -C {os.path.join(_HERE, "csrc")}`). There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    lib.pwv_version.restype = c.c_int
+    lib.pwv_last_error.restype = c.c_char_p
+    lib.pwv_device_count.restype = c.c_int
+    lib.pwv_model_create.argtypes = [c.POINTER(PwvHparams), c.POINTER(c.c_void_p)]
+    lib.pwv_model_destroy.argtypes = [c.c_void_p]
+    lib.pwv_model_num_variables.argtypes = [c.c_void_p]
+    lib.pwv_model_variable.argtypes = [c.c_void_p, c.c_int, c.POINTER(c.c_char_p), c.POINTER(c.c_int64), c.POINTER(c.c_int)]
+    lib.pwv_model_load_weight.argtypes = [c.c_void_p, c.c_char_p, c.c_void_p, c.POINTER(c.c_int64), c.c_int]
+    lib.pwv_model_finalize.argtypes = [c.c_void_p]
+    lib.pwv_workspace_bytes.argtypes = [c.c_void_p, c.c_int, c.c_int, c.POINTER(c.c_size_t)]
+    lib.pwv_forward.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t,
+                                c.c_int, c.c_int, c.c_void_p, c.POINTER(PwvTaps)]
+    lib.pwv_forward_host.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p]
+    lib.pwv_last_launch_count.argtypes = [c.c_void_p]
+    for name in EXPORTS:
+        if name not in ('pwv_last_error',):
+            getattr(lib, name).restype = c.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc < 0:
+        raise PwvError(rc, load().pwv_last_error().decode('utf-8', 'replace'))
+    return rc
+
+
+def make_hparams(dims, precision='fp32'):
+    """`dims` is weights.model_dims(hp)."""
+    if precision not in PREC:
+        raise ValueError(f'engine.precision must be one of {sorted(PREC)}, got {precision!r}')
+    h = PwvHparams()
+    h.n_iaf = dims['n_iaf']
+    h.filter_width = dims['k']
+    h.residual_channels = dims['R']
+    h.dilation_channels = dims['D']
+    h.skip_channels = dims['S']
+    h.condition_channels = dims['Cc']
+    h.n_mels = dims['n_mels']
+    h.hop_length = dims['hop']
+    h.use_biases = int(dims['use_biases'])
+    h.use_skip_connection = int(dims['use_skip'])
+    h.precision = PREC[precision]
+    if dims['n_iaf'] > PWV_MAX_FLOWS:
+        raise ValueError(f'n_iaf {dims["n_iaf"]} > {PWV_MAX_FLOWS}')
+    for i, dil in enumerate(dims['dilations']):
+        if len(dil) > PWV_MAX_LAYERS:
+            raise ValueError(f'flow {i}: {len(dil)} layers > {PWV_MAX_LAYERS}')
+        h.n_layers[i] = len(dil)
+        for j, d in enumerate(dil):
+            h.dilations[i][j] = int(d)
+    return h

@@ -1,0 +1,578 @@
+// pwv_api.cu -- C-ABI (include/pwv.h) of the B200-native IAF-vocoder generation path:
+// model/weight management and the launch sequence of one forward pass
+// (reference models.py:23-78 -> modules.py:53-60 -> modules.py:129-166).
+#include "../../include/pwv.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pwv_simt.cuh"
+#include "pwv_tc.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PWV_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(PWV_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                  cudaGetErrorString(e_));                                                    \
+  } while (0)
+
+struct VarSpec {
+  std::string name;
+  int64_t shape[3];
+  int ndim;
+  size_t numel() const {
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+    return n;
+  }
+};
+
+const char* kBodies[2] = {"scalar", "shifter"};   // reference models.py:48,63 (sic)
+}  // namespace
+
+// per (flow, body) offsets (in floats) into the device weight arena
+struct LayerOff {
+  size_t wfg, wd, bd, ws, bs;
+};
+struct BodyOff {
+  size_t causal;                 // [2][C]
+  std::vector<LayerOff> layers;
+  size_t w1, b1, w2, b2;
+};
+
+struct pwv_model {
+  pwv_hparams hp;
+  int C, S, Cc;
+  int total_layers;              // sum over flows
+  int max_layers;                // max over flows
+  std::vector<VarSpec> vars;
+  std::map<std::string, int> var_index;
+  std::vector<std::vector<float>> staged;
+  std::vector<char> loaded;
+  bool finalized = false;
+  int device = 0;
+
+  size_t off_wc = 0;             // cond dense [n_mels][Cc]
+  std::vector<BodyOff> bodies;   // [flow*2 + body]
+  float* d_arena = nullptr;
+  size_t arena_floats = 0;
+
+  // conditioning projections of a flow, contiguous so one batched GEMM covers them:
+  // off_wgc[flow] -> [2 bodies][L][Cc][2C]  ([gc_filter | gc_gate]),  off_bfg[flow] -> [2][L][2C]
+  std::vector<size_t> off_wgc, off_bfg;
+
+  pwv::TcModel tc;               // tensor-core weight images (empty in fp32 mode)
+
+  // host-buffer entry point staging
+  float* h_dev = nullptr;
+  size_t h_dev_bytes = 0;
+  int last_launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// variable list (the reference's creation order; shapes in TF layout)
+// ------------------------------------------------------------------------------------------------
+static void add_var(pwv_model* m, const std::string& name, std::initializer_list<int64_t> shape) {
+  VarSpec v;
+  v.name = name;
+  v.ndim = (int)shape.size();
+  int i = 0;
+  for (auto s : shape) v.shape[i++] = s;
+  for (; i < 3; ++i) v.shape[i] = 1;
+  m->var_index[name] = (int)m->vars.size();
+  m->vars.push_back(v);
+}
+
+static void build_var_list(pwv_model* m) {
+  const pwv_hparams& hp = m->hp;
+  const int64_t k = hp.filter_width, R = hp.residual_channels, D = hp.dilation_channels,
+                S = hp.skip_channels, Cc = hp.condition_channels;
+  add_var(m, "iaf_vocoder/cond/dense", {1, hp.n_mels, Cc});
+  for (int i = 0; i < hp.n_iaf; ++i)
+    for (int b = 0; b < 2; ++b) {
+      std::string p = "iaf_vocoder/iaf" + std::to_string(i) + "/" + kBodies[b];
+      add_var(m, p + "/causal_layer/filter", {k, 1, R});
+      for (int j = 0; j < hp.n_layers[i]; ++j) {
+        std::string q = p + "/dilated_stack/layer" + std::to_string(j);
+        add_var(m, q + "/filter", {k, R, D});
+        add_var(m, q + "/gate", {k, R, D});
+        add_var(m, q + "/gc_filter", {1, Cc, D});
+        add_var(m, q + "/gc_gate", {1, Cc, D});
+        if (hp.use_biases) {
+          add_var(m, q + "/filter_bias", {D});
+          add_var(m, q + "/gate_bias", {D});
+        }
+        add_var(m, q + "/dense", {1, D, R});
+        add_var(m, q + "/skip", {1, D, S});
+        if (hp.use_biases) {
+          add_var(m, q + "/dense_bias", {R});
+          add_var(m, q + "/skip_bias", {S});
+        }
+      }
+      std::string q = p + "/postprocessing";
+      add_var(m, q + "/postprocess1", {1, S, S});
+      if (hp.use_biases) add_var(m, q + "/postprocess1_bias", {S});
+      add_var(m, q + "/postprocess2", {1, S, 1});
+      if (hp.use_biases) add_var(m, q + "/postprocess2_bias", {1});
+    }
+  m->staged.resize(m->vars.size());
+  m->loaded.assign(m->vars.size(), 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pwv_version(void) { return PWV_VERSION; }
+const char* pwv_last_error(void) { return g_err; }
+
+int pwv_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(PWV_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
+  if (!hp || !out) return fail(PWV_EINVAL, "null argument");
+  *out = nullptr;
+  if (hp->n_iaf < 1 || hp->n_iaf > PWV_MAX_FLOWS) return fail(PWV_EINVAL, "n_iaf=%d out of range [1,%d]", hp->n_iaf, PWV_MAX_FLOWS);
+  if (hp->filter_width != 2) return fail(PWV_EINVAL, "filter_width=%d: only 2 is implemented", hp->filter_width);
+  if (hp->residual_channels != hp->dilation_channels)
+    return fail(PWV_EINVAL, "residual_channels (%d) must equal dilation_channels (%d)", hp->residual_channels, hp->dilation_channels);
+  if (hp->skip_channels != 2 * hp->residual_channels)
+    return fail(PWV_EINVAL, "skip_channels (%d) must equal 2*residual_channels (%d)", hp->skip_channels, 2 * hp->residual_channels);
+  const int C = hp->residual_channels;
+  if (C != 64 && C != 128 && C != 256) return fail(PWV_EINVAL, "residual_channels=%d: supported 64, 128, 256", C);
+  if (hp->use_skip_connection) return fail(PWV_EINVAL, "use_skip_connection=True is not implemented on the B200 path");
+  if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
+    return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
+  if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_TF32X3 && hp->precision != PWV_PREC_BF16)
+    return fail(PWV_EINVAL, "unknown precision %d", hp->precision);
+  if (hp->precision != PWV_PREC_FP32 && C != 64)
+    return fail(PWV_EINVAL, "tensor-core precisions are implemented for residual_channels=64 only (got %d)", C);
+  int total = 0, mx = 0;
+  for (int i = 0; i < hp->n_iaf; ++i) {
+    if (hp->n_layers[i] < 1 || hp->n_layers[i] > PWV_MAX_LAYERS) return fail(PWV_EINVAL, "flow %d: %d layers out of range [1,%d]", i, hp->n_layers[i], PWV_MAX_LAYERS);
+    for (int j = 0; j < hp->n_layers[i]; ++j)
+      if (hp->dilations[i][j] < 1) return fail(PWV_EINVAL, "flow %d layer %d: dilation %d < 1", i, j, hp->dilations[i][j]);
+    total += hp->n_layers[i];
+    mx = hp->n_layers[i] > mx ? hp->n_layers[i] : mx;
+  }
+  pwv_model* m = new (std::nothrow) pwv_model();
+  if (!m) return fail(PWV_ENOMEM, "out of host memory");
+  m->hp = *hp;
+  m->C = C;
+  m->S = hp->skip_channels;
+  m->Cc = hp->condition_channels;
+  m->total_layers = total;
+  m->max_layers = mx;
+  build_var_list(m);
+  *out = m;
+  return PWV_OK;
+}
+
+int pwv_model_destroy(pwv_model* m) {
+  if (!m) return PWV_OK;
+  if (m->d_arena) cudaFree(m->d_arena);
+  if (m->h_dev) cudaFree(m->h_dev);
+  pwv::tc_model_free(m->tc);
+  delete m;
+  return PWV_OK;
+}
+
+int pwv_model_num_variables(const pwv_model* m) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  return (int)m->vars.size();
+}
+
+int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[3], int* ndim) {
+  if (!m || index < 0 || index >= (int)m->vars.size()) return fail(PWV_EINVAL, "bad model/index");
+  const VarSpec& v = m->vars[index];
+  if (name) *name = v.name.c_str();
+  if (shape) for (int i = 0; i < 3; ++i) shape[i] = v.shape[i];
+  if (ndim) *ndim = v.ndim;
+  return PWV_OK;
+}
+
+int pwv_model_load_weight(pwv_model* m, const char* tf_name, const float* host_data, const int64_t* shape, int ndim) {
+  if (!m || !tf_name || !host_data || !shape) return fail(PWV_EINVAL, "null argument");
+  auto it = m->var_index.find(tf_name);
+  if (it == m->var_index.end()) return fail(PWV_ENAME, "unknown variable '%s'", tf_name);
+  const VarSpec& v = m->vars[it->second];
+  if (ndim != v.ndim) return fail(PWV_ENAME, "%s: ndim %d, expected %d", tf_name, ndim, v.ndim);
+  for (int i = 0; i < ndim; ++i)
+    if (shape[i] != v.shape[i]) return fail(PWV_ENAME, "%s: dim %d is %lld, expected %lld", tf_name, i, (long long)shape[i], (long long)v.shape[i]);
+  m->staged[it->second].assign(host_data, host_data + v.numel());
+  m->loaded[it->second] = 1;
+  m->finalized = false;
+  return PWV_OK;
+}
+
+static const std::vector<float>& var(const pwv_model* m, const std::string& name) {
+  return m->staged[m->var_index.at(name)];
+}
+
+int pwv_model_finalize(pwv_model* m) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  for (size_t i = 0; i < m->vars.size(); ++i)
+    if (!m->loaded[i]) return fail(PWV_ESTATE, "variable '%s' was not loaded", m->vars[i].name.c_str());
+  const pwv_hparams& hp = m->hp;
+  const int C = m->C, S = m->S, Cc = m->Cc;
+  std::vector<float> arena;
+  auto put = [&](size_t n) {   // 16-float (64 B) aligned blocks
+    size_t off = (arena.size() + 15) / 16 * 16;
+    arena.resize(off + n, 0.f);
+    return off;
+  };
+  m->off_wc = put((size_t)hp.n_mels * Cc);
+  {
+    const auto& w = var(m, "iaf_vocoder/cond/dense");
+    std::copy(w.begin(), w.end(), arena.begin() + m->off_wc);
+  }
+  m->bodies.assign(hp.n_iaf * 2, BodyOff());
+  m->off_wgc.assign(hp.n_iaf, 0);
+  m->off_bfg.assign(hp.n_iaf, 0);
+  for (int i = 0; i < hp.n_iaf; ++i) {
+    m->off_wgc[i] = put((size_t)2 * hp.n_layers[i] * Cc * 2 * C);
+    m->off_bfg[i] = put((size_t)2 * hp.n_layers[i] * 2 * C);
+    for (int b = 0; b < 2; ++b) {
+      BodyOff& bo = m->bodies[i * 2 + b];
+      std::string p = "iaf_vocoder/iaf" + std::to_string(i) + "/" + kBodies[b];
+      bo.causal = put(2 * C);
+      {
+        const auto& w = var(m, p + "/causal_layer/filter");   // [2][1][C]
+        std::copy(w.begin(), w.end(), arena.begin() + bo.causal);
+      }
+      bo.layers.resize(hp.n_layers[i]);
+      for (int j = 0; j < hp.n_layers[i]; ++j) {
+        LayerOff& lo = bo.layers[j];
+        std::string q = p + "/dilated_stack/layer" + std::to_string(j);
+        const auto& wf = var(m, q + "/filter");      // [2][C][C]
+        const auto& wg = var(m, q + "/gate");
+        lo.wfg = put((size_t)2 * C * 2 * C);
+        for (int tap = 0; tap < 2; ++tap)
+          for (int ci = 0; ci < C; ++ci)
+            for (int co = 0; co < C; ++co) {
+              size_t row = (size_t)tap * C + ci;   // tap 0 multiplies x[t-d], tap 1 x[t]
+              arena[lo.wfg + row * 2 * C + co] = wf[((size_t)tap * C + ci) * C + co];
+              arena[lo.wfg + row * 2 * C + C + co] = wg[((size_t)tap * C + ci) * C + co];
+            }
+        const auto& gf = var(m, q + "/gc_filter");   // [1][Cc][C]
+        const auto& gg = var(m, q + "/gc_gate");
+        const size_t wgc = m->off_wgc[i] + ((size_t)b * hp.n_layers[i] + j) * Cc * 2 * C;
+        const size_t bfg = m->off_bfg[i] + ((size_t)b * hp.n_layers[i] + j) * 2 * C;
+        for (int c = 0; c < Cc; ++c)
+          for (int co = 0; co < C; ++co) {
+            arena[wgc + (size_t)c * 2 * C + co] = gf[(size_t)c * C + co];
+            arena[wgc + (size_t)c * 2 * C + C + co] = gg[(size_t)c * C + co];
+          }
+        lo.wd = put((size_t)C * C);
+        lo.bd = put(C);
+        lo.ws = put((size_t)C * S);
+        lo.bs = put(S);
+        {
+          const auto& w = var(m, q + "/dense");
+          std::copy(w.begin(), w.end(), arena.begin() + lo.wd);
+          const auto& s = var(m, q + "/skip");
+          std::copy(s.begin(), s.end(), arena.begin() + lo.ws);
+        }
+        if (hp.use_biases) {
+          const auto& bf = var(m, q + "/filter_bias");
+          const auto& bg = var(m, q + "/gate_bias");
+          std::copy(bf.begin(), bf.end(), arena.begin() + bfg);
+          std::copy(bg.begin(), bg.end(), arena.begin() + bfg + C);
+          const auto& bd = var(m, q + "/dense_bias");
+          std::copy(bd.begin(), bd.end(), arena.begin() + lo.bd);
+          const auto& bs = var(m, q + "/skip_bias");
+          std::copy(bs.begin(), bs.end(), arena.begin() + lo.bs);
+        }
+      }
+      std::string q = p + "/postprocessing";
+      bo.w1 = put((size_t)S * S);
+      bo.b1 = put(S);
+      bo.w2 = put(S);
+      bo.b2 = put(1);
+      {
+        const auto& w1 = var(m, q + "/postprocess1");
+        std::copy(w1.begin(), w1.end(), arena.begin() + bo.w1);
+        const auto& w2 = var(m, q + "/postprocess2");
+        std::copy(w2.begin(), w2.end(), arena.begin() + bo.w2);
+        if (hp.use_biases) {
+          const auto& b1 = var(m, q + "/postprocess1_bias");
+          std::copy(b1.begin(), b1.end(), arena.begin() + bo.b1);
+          const auto& b2 = var(m, q + "/postprocess2_bias");
+          std::copy(b2.begin(), b2.end(), arena.begin() + bo.b2);
+        }
+      }
+    }
+  }
+  PWV_CUDA(cudaGetDevice(&m->device));
+  if (m->d_arena) { cudaFree(m->d_arena); m->d_arena = nullptr; }
+  m->arena_floats = arena.size();
+  PWV_CUDA(cudaMalloc(&m->d_arena, arena.size() * sizeof(float)));
+  PWV_CUDA(cudaMemcpy(m->d_arena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+  if (hp.precision != PWV_PREC_FP32) {
+    // tensor-core operand images are built from the same packed fp32 arena
+    std::vector<pwv::TcLayerSrc> src;
+    for (int i = 0; i < hp.n_iaf; ++i)
+      for (int b = 0; b < 2; ++b)
+        for (int j = 0; j < hp.n_layers[i]; ++j) {
+          const LayerOff& lo = m->bodies[i * 2 + b].layers[j];
+          pwv::TcLayerSrc s;
+          s.wfg = arena.data() + lo.wfg;
+          s.wd = arena.data() + lo.wd;
+          s.bd = arena.data() + lo.bd;
+          src.push_back(s);
+        }
+    const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src);
+    if (err) return fail(PWV_ECUDA, "tensor-core weight images: %s", err);
+  }
+  m->finalized = true;
+  return PWV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving (all blocks 256-byte aligned)
+// ------------------------------------------------------------------------------------------------
+struct Workspace {
+  float* cproj;     // [N][t_mel][Cc]
+  float* cbias;     // [2][Lmax][N][t_mel][2C]
+  float* act[2];    // ping/pong, each [2][N][T][C]
+  float* ss;        // [2][N][T] scale, shift
+  float* x[2];      // [N][T] ping/pong
+  size_t bytes;
+};
+
+static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
+  const int C = m->C, t_mel = 1 + T / m->hp.hop_length;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += (bytes + 255) / 256 * 256;
+    return p;
+  };
+  w->cproj = (float*)take(sizeof(float) * (size_t)N * t_mel * m->Cc);
+  w->cbias = (float*)take(sizeof(float) * (size_t)2 * m->max_layers * N * t_mel * 2 * C);
+  w->act[0] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
+  w->act[1] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
+  w->ss = (float*)take(sizeof(float) * (size_t)2 * N * T);
+  w->x[0] = (float*)take(sizeof(float) * (size_t)N * T);
+  w->x[1] = (float*)take(sizeof(float) * (size_t)N * T);
+  w->bytes = off;
+}
+
+static int check_shape(const pwv_model* m, int N, int T) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  if (N < 1 || T < 1) return fail(PWV_EINVAL, "N=%d, T=%d must be positive", N, T);
+  if (T % m->hp.hop_length != 0)
+    return fail(PWV_EINVAL, "length %d is not a multiple of hop_length %d (the reference's cond crop needs it, models.py:131-133)", T, m->hp.hop_length);
+  if (N > 65535) return fail(PWV_EINVAL, "N=%d exceeds the grid limit 65535", N);
+  return PWV_OK;
+}
+
+int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes) {
+  int rc = check_shape(m, N, T);
+  if (rc) return rc;
+  if (!bytes) return fail(PWV_EINVAL, "null bytes");
+  Workspace w;
+  carve(m, N, T, nullptr, &w);
+  *bytes = w.bytes;
+  return PWV_OK;
+}
+
+}  // extern "C"
+
+template <int C>
+static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st,
+                              const pwv_taps* taps, int* cur_buf, int* launches) {
+  using Cfg = pwv::TileCfg<C>;
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
+  int cur = *cur_buf;
+  for (int j = 0; j < L; ++j) {
+    pwv::LayerParams p;
+    p.x_in = w.act[cur];
+    p.x_out = w.act[cur ^ 1];
+    for (int b = 0; b < 2; ++b) {
+      const LayerOff& lo = m->bodies[flow * 2 + b].layers[j];
+      p.wfg[b] = m->d_arena + lo.wfg;
+      p.wd[b] = m->d_arena + lo.wd;
+      p.bd[b] = m->d_arena + lo.bd;
+      p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
+    }
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
+    p.mode = (j == L - 1) ? 1 : 0;
+    pwv::k_layer_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    ++*launches;
+    cur ^= 1;
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
+      PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * N * T * C,
+                               sizeof(float) * (size_t)N * T * C, cudaMemcpyDeviceToDevice, st));
+  }
+  // post-net on z (in act[cur])
+  pwv::PostParams q;
+  q.z = w.act[cur];
+  for (int b = 0; b < 2; ++b) {
+    const BodyOff& bo = m->bodies[flow * 2 + b];
+    const LayerOff& lo = bo.layers[L - 1];
+    q.ws[b] = m->d_arena + lo.ws; q.bs[b] = m->d_arena + lo.bs;
+    q.w1[b] = m->d_arena + bo.w1; q.b1[b] = m->d_arena + bo.b1;
+    q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
+  }
+  q.y = w.ss; q.N = N; q.T = T;
+  pwv::k_post_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  ++*launches;
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
+extern "C" {
+
+int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, void* workspace,
+                size_t workspace_bytes, int N, int T, pwv_stream stream, const pwv_taps* taps) {
+  int rc = check_shape(m, N, T);
+  if (rc) return rc;
+  if (!m->finalized) return fail(PWV_ESTATE, "pwv_model_finalize has not been called");
+  if (!noise || !mel || !wav || !workspace) return fail(PWV_EINVAL, "null buffer");
+  Workspace w;
+  carve(m, N, T, (char*)workspace, &w);
+  if (w.bytes > workspace_bytes) return fail(PWV_ENOMEM, "workspace has %zu bytes, %zu needed", workspace_bytes, w.bytes);
+  if (((uintptr_t)workspace & 255) != 0) return fail(PWV_EINVAL, "workspace must be 256-byte aligned");
+  const pwv_hparams& hp = m->hp;
+  const int C = m->C, Cc = m->Cc, t_mel = 1 + T / hp.hop_length;
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+
+  // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
+  {
+    pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, w.cproj, 0};
+    const int M = N * t_mel;
+    dim3 grid((Cc + 63) / 64, (M + 63) / 64, 1);
+    pwv::k_row_gemm<true><<<grid, 256, 0, st>>>(mel, rb, M, hp.n_mels, Cc);
+    ++launches;
+  }
+
+  int cur = 0, xcur = 0;
+  const float* x_prev = noise;
+  for (int i = 0; i < hp.n_iaf; ++i) {
+    const int L = hp.n_layers[i];
+    // per-layer conditioning terms of this flow: cbias[b][j] = cproj . [gc_filter|gc_gate] + [bf|bg]
+    {
+      pwv::RowGemmBatch rb{m->d_arena + m->off_wgc[i], (size_t)Cc * 2 * C, m->d_arena + m->off_bfg[i], (size_t)2 * C,
+                           w.cbias, (size_t)N * t_mel * 2 * C};
+      const int M = N * t_mel;
+      dim3 grid((2 * C + 63) / 64, (M + 63) / 64, 2 * L);
+      pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * C);
+      ++launches;
+    }
+    // front: IAF combine of the previous flow + causal layers
+    {
+      pwv::FrontParams f;
+      f.x_prev = x_prev;
+      f.scale = i == 0 ? nullptr : w.ss;
+      f.shift = i == 0 ? nullptr : w.ss + (size_t)N * T;
+      f.x_new = w.x[xcur];
+      f.wc[0] = m->d_arena + m->bodies[i * 2 + 0].causal;
+      f.wc[1] = m->d_arena + m->bodies[i * 2 + 1].causal;
+      f.act = w.act[cur];
+      f.N = N; f.T = T; f.C = C;
+      const size_t total = (size_t)N * T * (C / 4);
+      pwv::k_front<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      ++launches;
+      x_prev = w.x[xcur];
+      xcur ^= 1;
+    }
+    if (hp.precision == PWV_PREC_FP32) {
+      if (C == 64) rc = launch_layers_simt<64>(m, w, i, N, T, st, taps, &cur, &launches);
+      else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
+      else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
+    } else {
+      rc = fail(PWV_EINVAL, "tensor-core path not wired yet");
+    }
+    if (rc) return rc;
+    if (taps && taps->scale_shift)
+      PWV_CUDA(cudaMemcpyAsync(taps->scale_shift + (size_t)i * 2 * N * T, w.ss, sizeof(float) * 2 * (size_t)N * T, cudaMemcpyDeviceToDevice, st));
+    if (taps && taps->flow_out) {
+      const size_t n = (size_t)N * T;
+      pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, taps->flow_out + (size_t)i * n, n);
+      ++launches;
+    }
+  }
+  {
+    const size_t n = (size_t)N * T;
+    pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, wav, n);
+    ++launches;
+  }
+  PWV_CUDA(cudaGetLastError());
+  m->last_launches = launches;
+  return PWV_OK;
+}
+
+int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* wav, int N, int T, pwv_stream stream) {
+  int rc = check_shape(m, N, T);
+  if (rc) return rc;
+  if (!noise || !mel || !wav) return fail(PWV_EINVAL, "null buffer");
+  const int t_mel = 1 + T / m->hp.hop_length;
+  size_t ws = 0;
+  rc = pwv_workspace_bytes(m, N, T, &ws);
+  if (rc) return rc;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_noise = al(sizeof(float) * (size_t)N * T), b_mel = al(sizeof(float) * (size_t)N * t_mel * m->hp.n_mels);
+  const size_t need = ws + 2 * b_noise + b_mel;
+  if (need > m->h_dev_bytes) {
+    if (m->h_dev) cudaFree(m->h_dev);
+    m->h_dev = nullptr;
+    m->h_dev_bytes = 0;
+    PWV_CUDA(cudaMalloc(&m->h_dev, need));
+    m->h_dev_bytes = need;
+  }
+  char* base = (char*)m->h_dev;
+  float* d_noise = (float*)(base + ws);
+  float* d_wav = (float*)(base + ws + b_noise);
+  float* d_mel = (float*)(base + ws + 2 * b_noise);
+  cudaStream_t st = (cudaStream_t)stream;
+  PWV_CUDA(cudaMemcpyAsync(d_noise, noise, sizeof(float) * (size_t)N * T, cudaMemcpyHostToDevice, st));
+  PWV_CUDA(cudaMemcpyAsync(d_mel, mel, sizeof(float) * (size_t)N * t_mel * m->hp.n_mels, cudaMemcpyHostToDevice, st));
+  rc = pwv_forward(m, d_noise, d_mel, d_wav, base, ws, N, T, stream, nullptr);
+  if (rc) return rc;
+  PWV_CUDA(cudaMemcpyAsync(wav, d_wav, sizeof(float) * (size_t)N * T, cudaMemcpyDeviceToHost, st));
+  PWV_CUDA(cudaStreamSynchronize(st));
+  return PWV_OK;
+}
+
+int pwv_last_launch_count(const pwv_model* m) { return m ? m->last_launches : fail(PWV_EINVAL, "null model"); }
+
+}  // extern "C"

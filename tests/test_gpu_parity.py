@@ -1,0 +1,161 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs. Tolerance: |delta| <= 1e-4 per sample (BASELINE.json north_star, fp32)."""
+import numpy as np
+import pytest
+
+from conftest import pkg, small_case
+from oracle import iaf_oracle as O
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _run(hp, weights, noise, mel, taps=None, precision=None):
+    V = pkg('vocoder')
+    W = pkg('weights')
+    model = V.PwvModel(W.model_dims(hp), weights, precision or hp.engine.precision)
+    out = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda(), taps=taps)
+    torch.cuda.synchronize()
+    return out, model
+
+
+def _oracle(hp, weights, noise, mel, taps=None):
+    d = pkg('weights').model_dims(hp)
+    return O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], d['use_biases'], False,
+                                 dtype=np.float64, taps=taps)
+
+
+@pytest.mark.parametrize('channels', [64, 128, 256])
+def test_small_against_oracle_with_taps(hp, channels):
+    small_case(hp, channels=channels, t=1600 if channels == 64 else 800)
+    W = pkg('weights')
+    weights = W.init_weights(hp, seed=3, bias_std=0.1)
+    n, t = hp.generate.batch_size, hp.generate.length
+    noise, mel = O.synthetic_inputs(n, t, 80, 80)
+    taps = {}
+    ref = _oracle(hp, weights, noise, mel, taps)
+    (out, cap), _ = _run(hp, weights, noise, mel, taps={'flow_out': True, 'scale_shift': True, 'layer': (0, 1, 2)})
+    got_layer = cap['layer_out'].cpu().numpy()
+    want_layer = taps['iaf_vocoder/iaf0/shifter/dilated_stack/layer2']
+    assert np.abs(got_layer - want_layer).max() <= TOL
+    for i in range(len(hp.model.dilations)):
+        assert np.abs(cap['flow_out'][i].cpu().numpy() - taps[f'iaf_vocoder/iaf{i}']).max() <= TOL, i
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+def test_default_hparams_against_oracle(hp):
+    """Full default graph (4 flows, 120 gated layers), N=2, T=4000, non-zero biases."""
+    W = pkg('weights')
+    weights = W.init_weights(hp, seed=0, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(2, 4000, 80, 80)
+    ref = _oracle(hp, weights, noise, mel)
+    out, _ = _run(hp, weights, noise, mel)
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print('default hparams max|delta| =', err)
+    assert err <= TOL
+
+
+def test_stress_gain(hp):
+    """Kernels scaled x3 (pre-activations well into tanh/sigmoid saturation), zero biases."""
+    small_case(hp, dilations=((1, 2, 4, 8, 16, 32, 64, 128, 256, 512),), t=2400)
+    weights = pkg('weights').init_weights(hp, seed=5, gain=3.0)
+    noise, mel = O.synthetic_inputs(2, 2400, 80, 80)
+    ref = _oracle(hp, weights, noise, mel)
+    out, _ = _run(hp, weights, noise, mel)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL * scale
+
+
+@pytest.mark.parametrize('n,t', [(1, 80), (3, 240), (1, 4000), (5, 1040)])
+def test_edge_shapes(hp, n, t):
+    """Shortest legal length (one hop), dilation >= T (tap reads only zeros), lengths that are not
+    a multiple of the 64-row tile, odd batch."""
+    small_case(hp, dilations=((1, 512, 2), (256, 1)), n=n, t=t)
+    weights = pkg('weights').init_weights(hp, seed=7, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=11, noise_seed=12)
+    ref = _oracle(hp, weights, noise, mel)
+    out, _ = _run(hp, weights, noise, mel)
+    assert out.shape == (n, t)
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+def test_golden_fixture(hp):
+    """Committed fixture generated from the reference's own modules.py/models.py under the numpy
+    TF stand-in (tests/golden/make_golden_from_reference.py)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), 'golden', 'ref_small.npz')
+    if not os.path.exists(path):
+        pytest.skip('golden fixture not generated')
+    g = np.load(path, allow_pickle=False)
+    hp.set_hparam_dict({'model': {'n_iaf': int(g['n_iaf']), 'dilations': [list(map(int, d)) for d in g['dilations']]}},
+                       case='golden')
+    weights = {k[2:].replace('|', '/'): g[k] for k in g.files if k.startswith('w:')}
+    out, _ = _run(hp, weights, g['noise'], g['mel'])
+    assert np.abs(out.cpu().numpy() - g['wav']).max() <= TOL
+
+
+def test_properties_at_full_size(hp):
+    """BASELINE config c2 (N=8, T=16000, default hparams): size-independent properties.
+    (1) batch independence: utterance i alone == row i of the batch, bit for bit;
+    (2) causality: changing noise[t0:] and the mel frames after (t0+hop/2)//hop leaves wav[:t0]
+        bit-identical; (3) determinism."""
+    W = pkg('weights')
+    weights = W.init_weights(hp, seed=0, bias_std=0.05)
+    noise, mel = O.synthetic_inputs(8, 16000, 80, 80)
+    out, model = _run(hp, weights, noise, mel)
+    out = out.cpu().numpy()
+    assert np.isfinite(out).all()
+    again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()).cpu().numpy()
+    assert np.array_equal(out, again)
+    solo = model.forward(torch.from_numpy(noise[3:4]).cuda(), torch.from_numpy(mel[3:4]).cuda()).cpu().numpy()
+    assert np.array_equal(solo[0], out[3])
+    t0 = 9000
+    noise2, mel2 = noise.copy(), mel.copy()
+    noise2[:, t0:] += 1.0
+    mel2[:, (t0 + 40) // 80 + 1:, :] *= -1.0
+    out2 = model.forward(torch.from_numpy(noise2).cuda(), torch.from_numpy(mel2).cuda()).cpu().numpy()
+    assert np.array_equal(out2[:, :t0], out[:, :t0])
+    assert not np.array_equal(out2[:, t0:], out[:, t0:])
+
+
+def test_forward_host_matches_device_path(hp):
+    small_case(hp)
+    weights = pkg('weights').init_weights(hp, seed=3, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(2, 1600, 80, 80)
+    out, model = _run(hp, weights, noise, mel)
+    host = model.forward_host(noise, mel)
+    assert np.array_equal(host, out.cpu().numpy())
+    pinned_n = torch.from_numpy(noise).pin_memory()
+    pinned_m = torch.from_numpy(mel).pin_memory()
+    pinned_o = torch.empty((2, 1600), dtype=torch.float32).pin_memory()
+    model.forward_host(pinned_n, pinned_m, pinned_o)
+    assert np.array_equal(pinned_o.numpy(), host)
+
+
+def test_vocoder_call_surface(hp):
+    """IAFVocoder(batch, length)(wav, melspec, is_training=False) -> (N, length, 1) like models.py:78."""
+    small_case(hp)
+    V = pkg('vocoder')
+    model = V.IAFVocoder(batch_size=2, length=1600)
+    noise, mel = O.synthetic_inputs(2, 1600, 80, 80)
+    y = model(None, mel, is_training=False, noise=noise)
+    assert tuple(y.shape) == (2, 1600, 1) and y.dtype == torch.float32
+    ref = _oracle(hp, model.weights, noise, mel)
+    assert np.abs(y[:, :, 0].cpu().numpy() - ref).max() <= TOL
+    y2 = model(None, mel, is_training=False, noise_seed=5)     # in-graph style sampled noise
+    assert torch.isfinite(y2).all()
+    with pytest.raises(NotImplementedError):
+        model(None, mel, is_training=True)
+
+
+def test_errors_are_loud(hp):
+    L = pkg('_lib')
+    V = pkg('vocoder')
+    small_case(hp)
+    weights = pkg('weights').init_weights(hp, seed=3)
+    model = V.PwvModel(pkg('weights').model_dims(hp), weights)
+    noise = torch.zeros((1, 120), device='cuda')
+    mel = torch.zeros((1, 2, 80), device='cuda')
+    with pytest.raises(L.PwvError):          # 120 % 80 != 0
+        model.forward(noise, mel)
