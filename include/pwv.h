@@ -122,6 +122,13 @@ int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* 
 /* Kernel launches enqueued by the most recent pwv_forward on this model (for bench accounting). */
 int pwv_last_launch_count(const pwv_model* m);
 
+/* Per-kernel timing for the roofline report. While enabled, pwv_forward brackets every gated-layer
+ * kernel launch (the dominant kernel) with CUDA events on `stream`. pwv_profile_read waits for the
+ * most recent forward and returns the summed device time of those launches, their count, and the
+ * device time of the whole forward. */
+int pwv_set_profiling(pwv_model* m, int enable);
+int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double* forward_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,184 @@
+"""numpy stand-in for the dozen TensorFlow-1.x ops the reference's generation graph calls
+(reference modules.py:11-60,129-270; models.py:23-78,105-136) -- TEST INFRASTRUCTURE ONLY.
+
+It exists so that the reference's OWN `modules.py` / `models.py` can be imported and executed in
+this container (TensorFlow 1.x cannot be installed) to produce golden vectors: the model wiring,
+variable names and op order then come from the reference's source, only the op kernels below are
+restated. Each op evaluates eagerly on numpy arrays; `tf.get_variable` resolves names through the
+active `variable_scope` stack against a weight dict installed with `set_variables`.
+"""
+import contextlib
+import types
+
+import numpy as np
+
+float32 = np.float32
+AUTO_REUSE = object()
+
+_scope = []
+_variables = {}
+_created = []          # names in creation order (the reference's variable list)
+_logistic_sample = [None]
+
+
+def set_variables(mapping):
+    _variables.clear()
+    _variables.update(mapping)
+    del _created[:]
+
+
+def created_variables():
+    return list(_created)
+
+
+def set_logistic_sample(array):
+    _logistic_sample[0] = array
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None, **_):
+    _scope.append(name)
+    try:
+        yield
+    finally:
+        _scope.pop()
+
+
+name_scope = variable_scope
+
+
+def zeros_initializer(*a, **k):
+    return 'zeros'
+
+
+def ones_initializer(*a, **k):
+    return 'ones'
+
+
+def get_variable(name, shape=None, initializer=None, trainable=True, **_):
+    full = '/'.join(_scope + [name])
+    if full not in _variables:
+        raise KeyError('tf_shim: no value for variable ' + full)
+    value = np.asarray(_variables[full])
+    if shape is not None and tuple(int(s) for s in shape) != value.shape:
+        raise ValueError('tf_shim: %s has shape %s, graph asks for %s' % (full, value.shape, tuple(shape)))
+    if full not in _created:
+        _created.append(full)
+    return value
+
+
+def trainable_variables(scope=None):
+    return [n for n in _created if scope is None or n.startswith(scope)]
+
+
+def add_to_collection(*a, **k):
+    return None
+
+
+class GraphKeys(object):
+    UPDATE_OPS = 'update_ops'
+
+
+def shape(x):
+    return tuple(int(s) for s in np.shape(x))
+
+
+def div(a, b):
+    return a // b
+
+
+def pad(value, paddings, **_):
+    return np.pad(value, [tuple(int(v) for v in p) for p in paddings])
+
+
+def reshape(x, shape, **_):
+    return np.reshape(x, [int(s) for s in shape])
+
+
+def transpose(x, perm=None, **_):
+    return np.transpose(x, perm)
+
+
+def slice(x, begin, size, **_):     # noqa: A001 (mirrors tf.slice)
+    idx = []
+    for b, s, dim in zip(begin, size, np.shape(x)):
+        idx.append(np.s_[int(b):(dim if int(s) == -1 else int(b) + int(s))])
+    return x[tuple(idx)]
+
+
+def tile(x, multiples, **_):
+    return np.tile(x, [int(m) for m in multiples])
+
+
+def expand_dims(x, axis, **_):
+    return np.expand_dims(x, axis)
+
+
+def squeeze(x, axis=None, **_):
+    return np.squeeze(x, axis)
+
+
+def tanh(x, **_):
+    return np.tanh(x)
+
+
+def sigmoid(x, **_):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def add(a, b, **_):
+    return a + b
+
+
+def _conv1d(value, filters, stride=1, padding='VALID', name=None, **_):
+    """tf.nn.conv1d: out[n,t,co] = sum_j sum_ci in[n, t*stride + j, ci] * filters[j, ci, co]
+    over the (SAME: zero-padded) input; VALID keeps only fully covered positions."""
+    assert stride == 1
+    k = filters.shape[0]
+    if padding == 'SAME':
+        total = k - 1
+        value = np.pad(value, [(0, 0), (total // 2, total - total // 2), (0, 0)])
+    else:
+        assert padding == 'VALID'
+    t_out = value.shape[1] - k + 1
+    out = np.zeros((value.shape[0], t_out, filters.shape[2]), dtype=np.result_type(value, filters))
+    for j in range(k):
+        out = out + np.einsum('ntc,co->nto', value[:, j:j + t_out, :], filters[j])
+    return out
+
+
+def _relu(x, **_):
+    return np.maximum(x, 0)
+
+
+nn = types.SimpleNamespace(conv1d=_conv1d, relu=_relu)
+
+
+class _EMA(object):
+    def __init__(self, decay=None, **_):
+        self.decay = decay
+
+    def apply(self, var_list=None):
+        return None
+
+    def average_name(self, var):
+        return str(var) + '/ExponentialMovingAverage'
+
+
+train = types.SimpleNamespace(ExponentialMovingAverage=_EMA)
+
+
+class _Logistic(object):
+    def __init__(self, loc=0., scale=1.):
+        assert loc == 0. and scale == 1.
+
+    def sample(self, shape):
+        s = _logistic_sample[0]
+        if s is None:
+            raise RuntimeError('tf_shim: set_logistic_sample() first')
+        return np.reshape(s, [int(v) for v in shape])
+
+
+from . import contrib  # noqa: E402  (tensorflow.contrib.{distributions,signal})
+
+contrib.distributions.Logistic = _Logistic

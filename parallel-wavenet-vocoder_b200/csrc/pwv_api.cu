@@ -89,7 +89,28 @@ struct pwv_model {
   float* h_dev = nullptr;
   size_t h_dev_bytes = 0;
   int last_launches = 0;
+
+  // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
+  int ev_used = 0;
 };
+
+static cudaEvent_t prof_event(pwv_model* m) {
+  if (m->ev_used == (int)m->ev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    m->ev.push_back(e);
+  }
+  return m->ev[m->ev_used++];
+}
+#define PWV_PROF_MARK(m, st)                                  \
+  do {                                                        \
+    if ((m)->profiling) {                                     \
+      cudaEvent_t e_ = prof_event(m);                         \
+      if (e_) cudaEventRecord(e_, st);                        \
+    }                                                         \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // variable list (the reference's creation order; shapes in TF layout)
@@ -199,6 +220,7 @@ int pwv_model_destroy(pwv_model* m) {
   if (!m) return PWV_OK;
   if (m->d_arena) cudaFree(m->d_arena);
   if (m->h_dev) cudaFree(m->h_dev);
+  for (auto e : m->ev) cudaEventDestroy(e);
   pwv::tc_model_free(m->tc);
   delete m;
   return PWV_OK;
@@ -434,7 +456,9 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
     }
     p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : 0;
+    PWV_PROF_MARK(m, st);
     pwv::k_layer_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    PWV_PROF_MARK(m, st);
     ++*launches;
     cur ^= 1;
     if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
@@ -475,6 +499,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   const int C = m->C, Cc = m->Cc, t_mel = 1 + T / hp.hop_length;
   cudaStream_t st = (cudaStream_t)stream;
   int launches = 0;
+  m->ev_used = 0;
+  PWV_PROF_MARK(m, st);   // [0] forward start
+  PWV_PROF_MARK(m, st);   // [1] placeholder, re-recorded at the end
 
   // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
   {
@@ -536,6 +563,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, wav, n);
     ++launches;
   }
+  if (m->profiling && m->ev.size() >= 2) cudaEventRecord(m->ev[1], st);
   PWV_CUDA(cudaGetLastError());
   m->last_launches = launches;
   return PWV_OK;
@@ -574,5 +602,31 @@ int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* 
 }
 
 int pwv_last_launch_count(const pwv_model* m) { return m ? m->last_launches : fail(PWV_EINVAL, "null model"); }
+
+int pwv_set_profiling(pwv_model* m, int enable) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  m->profiling = enable != 0;
+  m->ev_used = 0;
+  return PWV_OK;
+}
+
+int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double* forward_ms) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  if (!m->profiling || m->ev_used < 2) return fail(PWV_ESTATE, "profiling is off or no forward has run since it was enabled");
+  PWV_CUDA(cudaEventSynchronize(m->ev[1]));
+  float ms = 0.f;
+  PWV_CUDA(cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]));
+  if (forward_ms) *forward_ms = ms;
+  double sum = 0.0;
+  int n = 0;
+  for (int i = 2; i + 1 < m->ev_used; i += 2) {
+    PWV_CUDA(cudaEventElapsedTime(&ms, m->ev[i], m->ev[i + 1]));
+    sum += ms;
+    ++n;
+  }
+  if (layer_ms) *layer_ms = sum;
+  if (layer_launches) *layer_launches = n;
+  return PWV_OK;
+}
 
 }  // extern "C"

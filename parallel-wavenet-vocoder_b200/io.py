@@ -1,0 +1,92 @@
+"""Inputs and outputs either side of the forward pass of `generate.py`.
+
+* `GenerationData`: the generation split of the dataset (reference data_load.py:18-25: sorted glob,
+  last 10 % when more than one file). `data_path: synthetic` yields the bench inputs instead
+  (mel ~ U(-1,1) as reference audio.py:278-286 normalises to, logistic noise). Reading real audio
+  needs the mel front end (librosa in the reference), which is upstream of this build's scope;
+  it raises with a clear message.
+* `find_checkpoint` / `load_checkpoint`: weights from `hp.logdir`. This build's container is a
+  `.npz` keyed by TF variable names (weights.py); TensorFlow bundle files (`model-*.index/.data`)
+  are recognised and reported as not yet readable.
+* `write_audio_summaries`: `audio/pred`, `audio/gt` into a TensorBoard event file in `hp.logdir`
+  (reference generate.py:41-45,71-73) when tensorboard is importable, plus `.npy` copies.
+"""
+import glob
+import os
+
+import numpy as np
+import torch
+
+from .hparam import hparam as hp
+
+
+class GenerationData:
+    def __init__(self, data_path, batch_size, length):
+        self.batch_size = int(batch_size)
+        self.length = int(length)
+        self.synthetic = (data_path == 'synthetic')
+        if self.synthetic:
+            self.wav_files = []
+            return
+        files = sorted(glob.glob(data_path))
+        if len(files) > 1:                                # reference data_load.py:22-23
+            split = int(len(files) * hp.train.dataset_ratio)
+            files = files[split:]
+        self.wav_files = files
+
+    def next_batch(self):
+        """-> (gt_wav (N,T,1) or None, melspec (N,t_mel,n_mels) f32, noise (N,T) f32 or None)"""
+        hop, n_mels = int(hp.signal.hop_length), int(hp.signal.n_mels)
+        n, t = self.batch_size, self.length
+        if self.synthetic:
+            engine = hp.get('engine', {}) or {}
+            mel = np.random.RandomState(1234).uniform(-1, 1, size=(n, 1 + t // hop, n_mels)).astype(np.float32)
+            u = np.random.RandomState(int(engine.get('noise_seed', 1235))).uniform(1e-7, 1 - 1e-7, size=(n, t))
+            noise = (np.log(u) - np.log1p(-u)).astype(np.float32)
+            return None, mel, noise
+        raise NotImplementedError(
+            'reading wav files needs the mel front end (reference data_load.py:37-56 -> audio.py:341-356, '
+            'librosa), which is outside this build; use a case with data_path: synthetic, or call '
+            'models.IAFVocoder directly with your own mel-spectrogram')
+
+
+def find_checkpoint(logdir, ckpt=None):
+    """`<logdir>/<ckpt>` when named (reference generate.py:55), else the newest weight file."""
+    if ckpt:
+        path = os.path.join(logdir, ckpt)
+        for cand in (path, path + '.npz'):
+            if os.path.exists(cand):
+                return cand
+        if glob.glob(path + '.index') or glob.glob(path + '.data-*'):
+            return path + '.index'
+        raise FileNotFoundError(path)
+    cands = sorted(glob.glob(os.path.join(logdir, '*.npz')), key=os.path.getmtime)
+    if cands:
+        return cands[-1]
+    tf_idx = sorted(glob.glob(os.path.join(logdir, '*.index')), key=os.path.getmtime)
+    return tf_idx[-1] if tf_idx else None
+
+
+def load_checkpoint(path, use_ema=False):
+    from . import weights as W
+    if path.endswith('.npz'):
+        return W.load_npz(path, use_ema=use_ema)
+    raise NotImplementedError(
+        f'{path}: TensorFlow bundle checkpoints are not readable yet; convert with '
+        f'`np.savez(path, **{{name.replace("/", "|"): value}})` keyed by TF variable names')
+
+
+def write_audio_summaries(logdir, sr, pred, gt=None):
+    os.makedirs(logdir, exist_ok=True)
+    pred = np.asarray(pred, dtype=np.float32)
+    np.save(os.path.join(logdir, 'pred_wav.npy'), pred)
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+    except Exception:           # tensorboard not installed: the .npy copy is the sink
+        return
+    writer = SummaryWriter(logdir)
+    for i in range(min(pred.shape[0], 3)):               # tf.summary.audio default max_outputs=3
+        writer.add_audio('audio/pred/%d' % i, torch.from_numpy(pred[i].reshape(1, -1)).clamp(-1, 1), 0, sample_rate=int(sr))
+        if gt is not None:
+            writer.add_audio('audio/gt/%d' % i, torch.as_tensor(gt[i]).reshape(1, -1).clamp(-1, 1), 0, sample_rate=int(sr))
+    writer.close()

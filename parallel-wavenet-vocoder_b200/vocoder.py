@@ -129,6 +129,15 @@ class PwvModel:
     def last_launch_count(self):
         return _lib.check(self.lib.pwv_last_launch_count(self._h))
 
+    def set_profiling(self, enable):
+        _lib.check(self.lib.pwv_set_profiling(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """-> (summed ms of the gated-layer launches, their count, ms of the whole forward)."""
+        layer_ms, n, fwd = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
+        _lib.check(self.lib.pwv_profile_read(self._h, ctypes.byref(layer_ms), ctypes.byref(n), ctypes.byref(fwd)))
+        return layer_ms.value, n.value, fwd.value
+
 
 def _as_host(a):
     if isinstance(a, torch.Tensor):

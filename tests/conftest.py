@@ -34,3 +34,19 @@ def small_case(hp, channels=64, dilations=((1, 2, 4, 512), (1, 8, 64)), n=2, t=1
         'engine': {'precision': precision},
     }, case='test/small')
     return hp
+
+
+def load_golden(hp, name):
+    """A committed fixture made by tests/golden/make_golden_from_reference.py: configures `hp`,
+    regenerates the weights from the stored recipe and verifies their checksum."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', name), allow_pickle=False)
+    n_layers = [int(v) for v in g['n_layers']]
+    dil = [[int(v) for v in row[:n]] for row, n in zip(g['dilations'], n_layers)]
+    hp.set_hparam_dict({'model': {'n_iaf': int(g['n_iaf']), 'dilations': dil}}, case='golden/' + name)
+    seed, bias_std, gain = g['weight_recipe']
+    weights = pkg('weights').init_weights(hp, seed=int(seed), bias_std=float(bias_std), gain=float(gain))
+    flat = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in weights.values()])
+    chk = np.array([flat.sum(), np.abs(flat).sum(), flat[::9973].sum()])
+    assert np.allclose(chk, g['weight_checksum'], rtol=0, atol=1e-9), 'regenerated weights differ from the fixture recipe'
+    return weights, g['noise'], g['mel'], g['wav'], dil

@@ -1,0 +1,128 @@
+"""The C-ABI library loads, exports every symbol include/pwv.h declares, validates hparams and
+variable names on the host, and FAILS LOUDLY (no fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg, small_case
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, 'include', 'pwv.h')) as fh:
+        text = fh.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(pwv_[a-z_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = pkg('_lib')
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(L.EXPORTS) == declared
+    assert lib.pwv_version() == 100
+
+
+def test_hparams_struct_matches_header():
+    L = pkg('_lib')
+    # 11 scalars + 8 + 8*64 int32
+    assert ctypes.sizeof(L.PwvHparams) == 4 * (11 + 8 + 8 * 64)
+
+
+def _create(hp, precision='fp32'):
+    L = pkg('_lib')
+    lib = L.load()
+    h = ctypes.c_void_p()
+    hparams = L.make_hparams(pkg('weights').model_dims(hp), precision)
+    rc = lib.pwv_model_create(ctypes.byref(hparams), ctypes.byref(h))
+    return lib, h, rc
+
+
+def test_model_create_validates(hp):
+    L = pkg('_lib')
+    lib, h, rc = _create(hp)
+    assert rc == 0 and h.value
+    assert lib.pwv_model_num_variables(h) == 1241
+    name = ctypes.c_char_p()
+    shape = (ctypes.c_int64 * 3)()
+    ndim = ctypes.c_int()
+    assert lib.pwv_model_variable(h, 0, ctypes.byref(name), shape, ctypes.byref(ndim)) == 0
+    assert name.value == b'iaf_vocoder/cond/dense' and list(shape) == [1, 80, 80] and ndim.value == 3
+    names = []
+    for i in range(1241):
+        lib.pwv_model_variable(h, i, ctypes.byref(name), shape, ctypes.byref(ndim))
+        names.append(name.value.decode())
+    assert names == list(pkg('weights').variable_shapes(hp).keys())
+    lib.pwv_model_destroy(h)
+
+    hp.model.filter_width = 3
+    _, _, rc = _create(hp)
+    assert rc == -1 and b'filter_width' in lib.pwv_last_error()
+    hp.model.filter_width = 2
+    hp.model.use_skip_connection = True
+    _, _, rc = _create(hp)
+    assert rc == -1 and b'use_skip_connection' in lib.pwv_last_error()
+    hp.model.use_skip_connection = False
+    hp.model.residual_channels = 48
+    _, _, rc = _create(hp)
+    assert rc == -1
+    with pytest.raises(ValueError):
+        L.make_hparams(pkg('weights').model_dims(hp), 'fp16')
+
+
+def test_load_weight_checks_names_and_shapes(hp):
+    small_case(hp)
+    lib, h, rc = _create(hp)
+    assert rc == 0
+    w = np.zeros((1, 80, 80), np.float32)
+    shp = (ctypes.c_int64 * 3)(1, 80, 80)
+    assert lib.pwv_model_load_weight(h, b'iaf_vocoder/cond/dense', w.ctypes.data_as(ctypes.c_void_p), shp, 3) == 0
+    assert lib.pwv_model_load_weight(h, b'iaf_vocoder/cond/nope', w.ctypes.data_as(ctypes.c_void_p), shp, 3) == -5
+    bad = (ctypes.c_int64 * 3)(1, 80, 81)
+    assert lib.pwv_model_load_weight(h, b'iaf_vocoder/cond/dense', w.ctypes.data_as(ctypes.c_void_p), bad, 3) == -5
+    # finalize before everything is loaded is a state error naming the first missing variable
+    assert lib.pwv_model_finalize(h) == -2 and b'was not loaded' in lib.pwv_last_error()
+    lib.pwv_model_destroy(h)
+
+
+def test_workspace_query_and_shape_errors(hp):
+    lib, h, rc = _create(hp)
+    out = ctypes.c_size_t()
+    assert lib.pwv_workspace_bytes(h, 8, 16000, ctypes.byref(out)) == 0
+    # two ping/pong activation buffers of [2][N][T][64] fp32 dominate
+    assert out.value >= 2 * 2 * 8 * 16000 * 64 * 4
+    assert lib.pwv_workspace_bytes(h, 8, 16001, ctypes.byref(out)) == -1
+    assert b'hop_length' in lib.pwv_last_error()
+    lib.pwv_model_destroy(h)
+
+
+def test_no_cpu_fallback(hp):
+    """Without a CUDA device the product path must raise, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    small_case(hp)
+    L, V, W = pkg('_lib'), pkg('vocoder'), pkg('weights')
+    assert L.load().pwv_device_count() < 0
+    with pytest.raises(L.PwvError) as e:
+        V.PwvModel(W.model_dims(hp), W.init_weights(hp, seed=0))
+    assert e.value.code == -3
+    with pytest.raises(Exception):
+        V.IAFVocoder(batch_size=1, length=1600)
+
+
+def test_product_path_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg_dir = os.path.join(ROOT, 'parallel-wavenet-vocoder_b200')
+    offenders = []
+    for base in [pkg_dir] + [os.path.join(ROOT, f) for f in ('generate.py', 'generate_multi.py', 'models.py', 'hparam.py')]:
+        paths = [base] if os.path.isfile(base) else [os.path.join(d, f) for d, _, fs in os.walk(base) for f in fs if f.endswith(('.py', '.cu', '.cuh'))]
+        for p in paths:
+            if os.path.exists(p) and re.search(r'^\s*(from|import)\s+oracle\b|oracle[./]iaf_oracle', open(p).read(), flags=re.M):
+                offenders.append(p)
+    assert not offenders, offenders
