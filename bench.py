@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the IAF-vocoder generation path (audio samples/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+One "step" = one forward pass (noise + mel -> waveform, 4 IAF flows) over one batch. Workload at
+N=1: BASELINE.json configs[1] ("c2": batch = 8 utterances x 1 s @ 16 kHz, default hparams, fp32).
+N>1: the same batch PER GPU (weak scaling; utterances are independent, no data-path collective),
+launched by torchrun with one rank per GPU.
+
+Prints ONE JSON line (rank 0). `value` = whole-job samples/s with inputs resident in HBM, timed
+with CUDA events per step (L2 flushed between steps), max over ranks. `e2e` = the same metric
+through the C-ABI host-buffer call `pwv_forward_host` (pinned host inputs, H2D + kernels + D2H +
+sync inside the timed region). `roofline` = the gated-layer kernel's algorithmic bytes / its
+measured launch time against MEASURED_PEAKS.json. `cpu_baseline` = the numpy oracle (a port of
+the reference's TF-CPU path; TF itself is not installable) timed on this box's host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = 'parallel-wavenet-vocoder_b200'
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FALLBACK_BF16_TFLOPS = 1590.0
+
+WORKLOADS = {
+    # name: (case in hparams.yaml, description)
+    'c1': ('bench/c1', 'c1: batch=1 utt x 1 s (16000 samples), 16 kHz, default hparams'),
+    'c2': ('bench/c2', 'c2: batch=8 utt x 1 s (16000 samples) per GPU, 16 kHz, 4 IAF flows, default hparams'),
+    'c3': ('bench/c3', 'c3: batch=64 utt x 4 s (96000 samples) per GPU, 24 kHz, default hparams'),
+    'c4': ('bench/c4', 'c4: batch=256 utt x 1 s total, sharded over the GPUs'),
+}
+
+
+def pkg(mod):
+    return importlib.import_module(PKG + '.' + mod)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p['hbm_gbs']), bf16=float(p['bf16_tflops']),
+                    bf16_sustained=float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), source='measured')
+    return dict(hbm=FALLBACK_HBM_GBS, bf16=FALLBACK_BF16_TFLOPS, bf16_sustained=1400.0, source='fallback')
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            if not (t_begin - 0.05 <= ts <= t_end + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples in the timed region'], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': float(max(power))}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port timed on host cores
+# ------------------------------------------------------------------------------------------------
+_THREADS = {}
+
+
+def calibrate_threads(fn):
+    """All host cores are offered; these small-matrix ops scale badly past a socket's worth of
+    threads, so the fastest count among {all, 1/2, 1/4, ... >= 4} on a short probe is used (a CPU
+    arm that is slower with more threads would flatter the GPU side)."""
+    import torch
+    if 'best' in _THREADS:
+        return _THREADS['best']
+    cores = host_cores()
+    cands, c = [], cores
+    while c >= 4:
+        cands.append(c)
+        c //= 2
+    cands = cands or [cores]
+    best, best_t = cands[0], float('inf')
+    for c in cands:
+        torch.set_num_threads(c)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    _THREADS['best'] = best
+    return best
+
+
+def time_cpu_oracle(hp, n, t, repeats=1, warm=False):
+    """The numpy oracle (float32, BLAS on all host cores) on an (n, t) batch -> samples/s, seconds."""
+    from oracle import iaf_oracle as O
+    W = pkg('weights')
+    d = W.model_dims(hp)
+    weights = W.init_weights(hp, seed=0)
+    noise, mel = O.synthetic_inputs(n, t, d['hop'], d['n_mels'])
+    import torch
+    ops = O.TorchOps()                       # torch-CPU kernels (MKL + threaded elementwise)
+    threads = calibrate_threads(lambda: O.iaf_vocoder_forward(noise[:1, :d['hop'] * 20], mel[:1, :21], weights, d['dilations'],
+                                                             d['hop'], dtype=np.float32, ops=ops))
+    torch.set_num_threads(threads)
+    time_cpu_oracle.threads = threads
+    if warm:
+        O.iaf_vocoder_forward(noise[:1, :d['hop'] * 10], mel[:1, :11], weights, d['dilations'], d['hop'], dtype=np.float32, ops=ops)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], d['use_biases'], False, dtype=np.float32, ops=ops)
+        times.append(time.perf_counter() - t0)
+    return n * t / float(np.median(times)), times
+
+
+def run_reference_arm(args, hp, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path. TensorFlow 1.x cannot be
+    installed (no wheel for this Python, no network), so this is the oracle port, on all host
+    cores, one bounded sample (1 utterance of the workload's length) per step."""
+    if rank != 0:
+        return
+    n_s, t = 1, int(hp.generate.length)
+    t = min(t, 16000)
+    for _ in range(max(args.warmup, 0) and 1):      # one warm-up pass is enough for BLAS thread start
+        time_cpu_oracle(hp, 1, 1600)
+    _, times = time_cpu_oracle(hp, n_s, t, repeats=args.steps)
+    total = float(sum(times))
+    value = n_s * t * len(times) / total
+    cores = _THREADS.get('best', host_cores())
+    line = {
+        'impl': 'reference', 'metric': 'audio_samples_per_sec', 'value': value, 'unit': 'samples/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOADS[args.workload][1], 'sample': f'{n_s} utterance x {t} samples per step',
+                   'note': 'oracle port of the reference TF-CPU forward (oracle/iaf_oracle.py on torch-CPU kernels, all host threads); TF 1.x not installable'},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'cores_available': host_cores(), 'kind': 'port',
+                         'sample': f'{len(times)} x ({n_s} utt x {t} samples), default hparams, fp32'},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default=None, help="override engine.precision: fp32 | f16x3 | bf16")
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    hp = pkg('hparam').hparam
+    hp.set_hparam_yaml(WORKLOADS[args.workload][0])
+
+    if args.impl == 'reference':
+        run_reference_arm(args, hp, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f'bench.py: note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
+
+    V, W = pkg('vocoder'), pkg('weights')
+    from oracle import iaf_oracle as O          # synthetic input generator only (not the thing measured)
+    precision = args.precision or hp.engine.precision
+    dims = W.model_dims(hp)
+    n_total, t = int(hp.generate.batch_size), int(hp.generate.length)
+    n = n_total // world if args.workload == 'c4' else n_total      # c4 is strong-scaled, others weak
+    weights = W.init_weights(hp, seed=0)
+    model = V.PwvModel(dims, weights, precision)
+    noise_h, mel_h = O.synthetic_inputs(n, t, dims['hop'], dims['n_mels'], mel_seed=1234 + rank, noise_seed=1235 + rank)
+    noise = torch.from_numpy(noise_h).to(dev)
+    mel = torch.from_numpy(mel_h).to(dev)
+    out = torch.empty((n, t), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(ev0, ev1):
+        flush.fill_(1)                          # evict L2 (not timed)
+        ev0.record()
+        model.forward(noise, mel, out=out)
+        ev1.record()
+
+    for _ in range(args.warmup):
+        one_step(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_begin = time.time()
+    for ev0, ev1 in events:
+        one_step(ev0, ev1)
+    barrier()
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    samples_per_step = n * t * world
+    value = samples_per_step * args.steps / (total_ms * 1e-3)
+    launches = model.last_launch_count() * args.steps
+
+    # ---- roofline of the dominant kernel (gated dilated layer), separate profiled steps
+    pk = peaks()
+    model.set_profiling(True)
+    layer_ms, layer_n, fwd_ms = [], 0, []
+    for _ in range(3):
+        flush.fill_(1)
+        model.forward(noise, mel, out=out)
+        lm, ln, fm = model.profile_read()
+        layer_ms.append(lm); layer_n = ln; fwd_ms.append(fm)
+    model.set_profiling(False)
+    act_bytes = 4 if precision != 'bf16_act' else 2
+    bytes_per_launch = 2 * n * t * (2 * dims['R'] * act_bytes)           # 2 bodies x (read R + write R) per sample
+    avg_launch_s = float(np.median(layer_ms)) * 1e-3 / max(layer_n, 1)
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    mac_per_launch = 2 * n * t * (2 * dims['R'] * 2 * dims['D'] + dims['D'] * dims['R'])
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(precision, {}).get('dram_bytes_per_launch')
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
+                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layer (both bodies)',
+                'bytes_per_launch': bytes_per_launch, 'avg_launch_us': avg_launch_s * 1e6, 'launches_per_step': layer_n,
+                'share_of_step': float(np.median(layer_ms) / np.median(fwd_ms)),
+                'tflops_fp32_equiv': 2 * mac_per_launch / avg_launch_s / 1e12,
+                'note': 'compute-bound at this precision: see DESIGN.md (FLOP/B ~ 80 vs fp32 ridge ~ 10)'}
+
+    # ---- e2e through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        pin_n = torch.from_numpy(noise_h).pin_memory()
+        pin_m = torch.from_numpy(mel_h).pin_memory()
+        pin_o = torch.empty((n, t), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            model.forward_host(pin_n, pin_m, pin_o)
+        e2e_s = 0.0
+        steps_e2e = max(3, min(args.steps, 10))
+        barrier()
+        for _ in range(steps_e2e):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.forward_host(pin_n, pin_m, pin_o)      # H2D + kernels + D2H + sync inside
+            e2e_s += time.perf_counter() - t0
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {'value': samples_per_step * steps_e2e / float(tt.item()), 'unit': 'samples/s',
+               'h2d_bytes_per_step': int(noise_h.nbytes + mel_h.nbytes) * world, 'd2h_bytes_per_step': int(n * t * 4) * world,
+               'steps': steps_e2e, 'api': 'pwv_forward_host (pinned host buffers)'}
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sn, st = min(n, 8), min(t, 16000)
+        cps, times = time_cpu_oracle(hp, sn, st, repeats=1, warm=True)
+        cpu = {'value': cps, 'unit': 'samples/s', 'cores': _THREADS.get('best', host_cores()), 'cores_available': host_cores(), 'kind': 'port',
+               'sample': f'1 pass over {sn} utt x {st} samples (the {args.workload} batch), oracle port on torch-CPU kernels, fp32, {times[0]:.1f} s'}
+
+    if rank == 0:
+        line = {
+            'metric': 'audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'strong' if args.workload == 'c4' else 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'f16x3': 'f32 (fp16 hi/lo 3-term tensor-core split, fp32 accumulate)', 'bf16': 'bf16'}[precision],
+            'data': 'synthetic',
+            'config': {'workload': WORKLOADS[args.workload][1], 'per_gpu_batch': n, 'length': t, 'precision': precision,
+                       'l2': 'flushed (256 MB write) before every timed step', 'timing': 'CUDA events per step, max over ranks'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -54,8 +54,9 @@ extern "C" {
 
 /* arithmetic of the gated-layer contractions */
 #define PWV_PREC_FP32 0          /* fp32 FFMA on CUDA cores; bit-for-bit IEEE fp32 accumulate    */
-#define PWV_PREC_TF32X3 1        /* tcgen05 kind::tf32, 3-term split (fp32-level parity)         */
-#define PWV_PREC_BF16 2          /* tcgen05 kind::f16 bf16 operands, fp32 accumulate            */
+#define PWV_PREC_F16X3 1         /* tcgen05 kind::f16, fp16 hi/lo 3-term split, fp32 accumulate: */
+                                 /*   22-bit operands, fp32-level parity                        */
+#define PWV_PREC_BF16 2          /* tcgen05 kind::f16, single pass on bf16 operands, fp32 acc.  */
 
 typedef struct pwv_model pwv_model;   /* opaque */
 typedef void* pwv_stream;             /* a cudaStream_t / CUstream (0 = legacy default stream) */

@@ -25,6 +25,55 @@ import numpy as np
 ROOT = 'iaf_vocoder'
 
 
+# ----------------------------------------------------------------------------- array backends
+class NumpyOps:
+    """Default backend: numpy (float64 ground truth / float32)."""
+    name = 'numpy'
+    tanh = staticmethod(np.tanh)
+    exp = staticmethod(np.exp)
+    zeros_like = staticmethod(np.zeros_like)
+
+    @staticmethod
+    def relu(x):
+        return np.maximum(x, 0)
+
+    @staticmethod
+    def asarray(x, dtype):
+        return np.asarray(x, dtype=dtype)
+
+    @staticmethod
+    def tile_last(x, reps):
+        return np.tile(x, [1, 1, reps])
+
+    @staticmethod
+    def to_numpy(x):
+        return x
+
+
+class TorchOps:
+    """Same restatement evaluated by torch's CPU kernels (MKL matmul, threaded elementwise): the
+    kernel family TF-CPU would use. Only bench.py's CPU-baseline legs use it, for a fair timing."""
+    name = 'torch-cpu'
+
+    def __init__(self):
+        import torch
+        self.t = torch
+        self.tanh, self.exp, self.zeros_like, self.relu = torch.tanh, torch.exp, torch.zeros_like, torch.relu
+
+    def asarray(self, x, dtype):
+        return self.t.as_tensor(np.asarray(x, dtype=dtype))
+
+    def tile_last(self, x, reps):
+        return x.repeat(1, 1, reps)
+
+    @staticmethod
+    def to_numpy(x):
+        return x.numpy()
+
+
+_OPS = NumpyOps()
+
+
 # ----------------------------------------------------------------------------- causal_conv
 def conv1d_valid(x, w):
     """tf.nn.conv1d(x, w, stride=1, padding='VALID'): cross-correlation
@@ -70,7 +119,7 @@ def causal_conv(x, w, dilation):
         if shift == 0:
             term = x @ w[j]
         else:
-            xs = np.zeros_like(x)
+            xs = _OPS.zeros_like(x)
             if shift < t:
                 xs[:, shift:, :] = x[:, :t - shift, :]
             term = xs @ w[j]
@@ -86,11 +135,11 @@ def conv1x1(x, w):
 
 # ----------------------------------------------------------------------------- WaveNet body
 def _tanh(x):
-    return np.tanh(x)
+    return _OPS.tanh(x)
 
 
 def _sigmoid(x):
-    return 1.0 / (1.0 + np.exp(-x))
+    return 1.0 / (1.0 + _OPS.exp(-x))
 
 
 def dilation_layer(cur, cond, W, prefix, dilation, use_biases):
@@ -129,11 +178,11 @@ def wavenet(x, cond, W, prefix, dilations, use_biases=True, use_skip_connection=
             total = total + o
     else:
         total = outputs[-1]
-    h = np.maximum(total, 0)                                                 # :148
+    h = _OPS.relu(total)                                                     # :148
     h = conv1x1(h, W[prefix + '/postprocessing/postprocess1'])               # :152-153
     if use_biases:
         h = h + W[prefix + '/postprocessing/postprocess1_bias']              # :155-156
-    h = np.maximum(h, 0)                                                     # :157
+    h = _OPS.relu(h)                                                         # :157
     y = conv1x1(h, W[prefix + '/postprocessing/postprocess2'])               # :161-162
     if use_biases:
         y = y + W[prefix + '/postprocessing/postprocess2_bias']              # :164-165
@@ -147,8 +196,8 @@ def upsample_cond_repeat(mel, w_dense, hop):
     `-hop // 2` (floor division of the negated value) at the back."""
     n, t_mel, _ = mel.shape
     cc = w_dense.shape[2]
-    cond = np.maximum(conv1x1(mel, w_dense), 0)                              # :129-130
-    cond = np.tile(cond, [1, 1, hop]).reshape(-1, t_mel * hop, cc)           # :131-132
+    cond = _OPS.relu(conv1x1(mel, w_dense))                                  # :129-130
+    cond = _OPS.tile_last(cond, hop).reshape(-1, t_mel * hop, cc)            # :131-132
     return cond[:, hop // 2: -hop // 2, :]                                   # :133
 
 
@@ -160,16 +209,25 @@ def logistic_noise(shape, seed, dtype=np.float64):
 
 
 def iaf_vocoder_forward(noise, mel, W, dilations, hop, use_biases=True, use_skip_connection=False,
-                        dtype=np.float64, taps=None):
+                        dtype=np.float64, taps=None, ops=None):
     """Reference models.py:23-78 (is_training=False, normalizers '', upsample 'repeat').
 
     noise (N,T) or (N,T,1): the logistic sample the reference draws in-graph (models.py:32-33) --
     an INPUT here so that both sides see the same numbers. mel (N, 1+T//hop, n_mels).
     W: name -> array in TF layout. dilations: list (per flow) of lists. Returns (N, T) `dtype`.
     """
-    W = {k: np.asarray(v, dtype=dtype) for k, v in W.items()}
-    mel = np.asarray(mel, dtype=dtype)
-    x = np.asarray(noise, dtype=dtype).reshape(noise.shape[0], noise.shape[1], 1)
+    global _OPS
+    prev_ops, _OPS = _OPS, (ops or NumpyOps())
+    try:
+        return _OPS.to_numpy(_forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dtype, taps))
+    finally:
+        _OPS = prev_ops
+
+
+def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dtype, taps):
+    W = {k: _OPS.asarray(v, dtype) for k, v in W.items()}
+    mel = _OPS.asarray(mel, dtype)
+    x = _OPS.asarray(noise, dtype).reshape(noise.shape[0], noise.shape[1], 1)
     n, t, _ = x.shape
     cond = upsample_cond_repeat(mel, W[f'{ROOT}/cond/dense'], hop)           # models.py:26
     if cond.shape[1] != t:
@@ -181,7 +239,7 @@ def iaf_vocoder_forward(noise, mel, W, dilations, hop, use_biases=True, use_skip
         shift = wavenet(x, cond, W, p + '/shifter', dil, use_biases, use_skip_connection, taps)
         x = x * scale + shift                                                # modules.py:57-59
         if taps is not None:
-            taps[p] = x[:, :, 0].copy()
+            taps[p] = _OPS.to_numpy(x[:, :, 0]).copy()
     return x[:, :, 0]
 
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libpwv_b200.so')
 
 PWV_MAX_FLOWS = 8
 PWV_MAX_LAYERS = 64
-PREC = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
+PREC = {'fp32': 0, 'f16x3': 1, 'bf16': 2}
 
 EXPORTS = (
     'pwv_version', 'pwv_last_error', 'pwv_device_count', 'pwv_model_create', 'pwv_model_destroy',

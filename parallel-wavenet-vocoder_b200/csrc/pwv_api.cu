@@ -82,6 +82,8 @@ struct pwv_model {
   // conditioning projections of a flow, contiguous so one batched GEMM covers them:
   // off_wgc[flow] -> [2 bodies][L][Cc][2C]  ([gc_filter | gc_gate]),  off_bfg[flow] -> [2][L][2C]
   std::vector<size_t> off_wgc, off_bfg;
+  size_t off_colscale = 0;       // [2C]: -2log2e (filter half), -log2e (gate half) for the tensor-core epilogue
+  int num_sms = 148;
 
   pwv::TcModel tc;               // tensor-core weight images (empty in fp32 mode)
 
@@ -191,7 +193,7 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (hp->use_skip_connection) return fail(PWV_EINVAL, "use_skip_connection=True is not implemented on the B200 path");
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
-  if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_TF32X3 && hp->precision != PWV_PREC_BF16)
+  if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_F16X3 && hp->precision != PWV_PREC_BF16)
     return fail(PWV_EINVAL, "unknown precision %d", hp->precision);
   if (hp->precision != PWV_PREC_FP32 && C != 64)
     return fail(PWV_EINVAL, "tensor-core precisions are implemented for residual_channels=64 only (got %d)", C);
@@ -275,6 +277,11 @@ int pwv_model_finalize(pwv_model* m) {
     const auto& w = var(m, "iaf_vocoder/cond/dense");
     std::copy(w.begin(), w.end(), arena.begin() + m->off_wc);
   }
+  m->off_colscale = put(2 * C);
+  for (int c = 0; c < C; ++c) {
+    arena[m->off_colscale + c] = pwv::TC_KF;
+    arena[m->off_colscale + C + c] = pwv::TC_KG;
+  }
   m->bodies.assign(hp.n_iaf * 2, BodyOff());
   m->off_wgc.assign(hp.n_iaf, 0);
   m->off_bfg.assign(hp.n_iaf, 0);
@@ -353,6 +360,7 @@ int pwv_model_finalize(pwv_model* m) {
     }
   }
   PWV_CUDA(cudaGetDevice(&m->device));
+  PWV_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
   if (m->d_arena) { cudaFree(m->d_arena); m->d_arena = nullptr; }
   m->arena_floats = arena.size();
   PWV_CUDA(cudaMalloc(&m->d_arena, arena.size() * sizeof(float)));
@@ -483,6 +491,69 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
   return PWV_OK;
 }
 
+
+// gated layers of one flow on the tensor cores; the post-net stays on the fp32 kernel
+static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st,
+                            const pwv_taps* taps, int* cur_buf, int* launches) {
+  constexpr int C = pwv::TC_C;
+  using Cfg = pwv::TileCfg<C>;
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
+  const bool bf16 = hp.precision == PWV_PREC_BF16;
+  auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
+  const int tiles_body = N * tiles_per_utt;
+  int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;
+  grid &= ~1;   // the two bodies get the same number of CTAs
+  if (grid < 2) grid = 2;
+  size_t layer_base = 0;   // index of (flow, body 0, layer 0) in the image array
+  for (int i = 0; i < flow; ++i) layer_base += 2 * (size_t)hp.n_layers[i];
+  int cur = *cur_buf;
+  for (int j = 0; j < L; ++j) {
+    pwv::TcLayerParams p;
+    p.x_in = w.act[cur];
+    p.x_out = w.act[cur ^ 1];
+    for (int b = 0; b < 2; ++b) {
+      p.image[b] = m->tc.d_images + (layer_base + (size_t)b * L + j) * pwv::TC_IMAGE_BYTES;
+      p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
+    }
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
+    p.mode = (j == L - 1) ? 1 : 0;
+    p.tiles_per_utt = tiles_per_utt;
+    PWV_PROF_MARK(m, st);
+    kern<<<grid, 288, pwv::TC_SMEM_BYTES, st>>>(p);
+    PWV_PROF_MARK(m, st);
+    ++*launches;
+    cur ^= 1;
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
+      PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * N * T * C,
+                               sizeof(float) * (size_t)N * T * C, cudaMemcpyDeviceToDevice, st));
+  }
+  pwv::PostParams q;
+  q.z = w.act[cur];
+  for (int b = 0; b < 2; ++b) {
+    const BodyOff& bo = m->bodies[flow * 2 + b];
+    const LayerOff& lo = bo.layers[L - 1];
+    q.ws[b] = m->d_arena + lo.ws; q.bs[b] = m->d_arena + lo.bs;
+    q.w1[b] = m->d_arena + bo.w1; q.b1[b] = m->d_arena + bo.b1;
+    q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
+  }
+  q.y = w.ss; q.N = N; q.T = T;
+  dim3 pgrid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
+  pwv::k_post_simt<C><<<pgrid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  ++*launches;
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
 extern "C" {
 
 int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, void* workspace,
@@ -505,7 +576,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
 
   // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
   {
-    pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, w.cproj, 0};
+    pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, w.cproj, 0, nullptr};
     const int M = N * t_mel;
     dim3 grid((Cc + 63) / 64, (M + 63) / 64, 1);
     pwv::k_row_gemm<true><<<grid, 256, 0, st>>>(mel, rb, M, hp.n_mels, Cc);
@@ -519,7 +590,8 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     // per-layer conditioning terms of this flow: cbias[b][j] = cproj . [gc_filter|gc_gate] + [bf|bg]
     {
       pwv::RowGemmBatch rb{m->d_arena + m->off_wgc[i], (size_t)Cc * 2 * C, m->d_arena + m->off_bfg[i], (size_t)2 * C,
-                           w.cbias, (size_t)N * t_mel * 2 * C};
+                           w.cbias, (size_t)N * t_mel * 2 * C,
+                           hp.precision == PWV_PREC_FP32 ? nullptr : m->d_arena + m->off_colscale};
       const int M = N * t_mel;
       dim3 grid((2 * C + 63) / 64, (M + 63) / 64, 2 * L);
       pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * C);
@@ -547,7 +619,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
     } else {
-      rc = fail(PWV_EINVAL, "tensor-core path not wired yet");
+      rc = launch_layers_tc(m, w, i, N, T, st, taps, &cur, &launches);
     }
     if (rc) return rc;
     if (taps && taps->scale_shift)

@@ -43,6 +43,7 @@ struct RowGemmBatch {
   const float* B;      size_t strideB;      // entry z: [K][Nc] at B + z*strideB
   const float* bias;   size_t strideBias;   // entry z: [Nc] (nullptr: no bias)
   float* out;          size_t strideOut;    // entry z: [M][Nc]
+  const float* colscale;                    // [Nc] applied after the bias (nullptr: none)
 };
 
 template <bool RELU>
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) k_row_gemm(const float* __restrict__ A, R
       int n = n0 + tx * 4 + j;
       if (n >= Nc) continue;
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (batch.colscale) v *= batch.colscale[n];
       if (RELU) v = fmaxf(v, 0.f);
       out[(size_t)m * Nc + n] = v;
     }
