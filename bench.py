@@ -129,14 +129,14 @@ _THREADS = {}
 
 def calibrate_threads(fn):
     """All host cores are offered; these small-matrix ops scale badly past a socket's worth of
-    threads, so the fastest count among {all, 1/2, 1/4, ... >= 4} on a short probe is used (a CPU
+    threads, so the fastest count among {all, 1/2, 1/4, ... >= 8} on a short probe is used (a CPU
     arm that is slower with more threads would flatter the GPU side)."""
     import torch
     if 'best' in _THREADS:
         return _THREADS['best']
     cores = host_cores()
     cands, c = [], cores
-    while c >= 4:
+    while c >= 8:
         cands.append(c)
         c //= 2
     cands = cands or [cores]
@@ -162,7 +162,7 @@ def time_cpu_oracle(hp, n, t, repeats=1, warm=False):
     noise, mel = O.synthetic_inputs(n, t, d['hop'], d['n_mels'])
     import torch
     ops = O.TorchOps()                       # torch-CPU kernels (MKL + threaded elementwise)
-    threads = calibrate_threads(lambda: O.iaf_vocoder_forward(noise[:1, :d['hop'] * 20], mel[:1, :21], weights, d['dilations'],
+    threads = calibrate_threads(lambda: O.iaf_vocoder_forward(noise[:1, :d['hop'] * 50], mel[:1, :51], weights, d['dilations'],
                                                              d['hop'], dtype=np.float32, ops=ops))
     torch.set_num_threads(threads)
     time_cpu_oracle.threads = threads
