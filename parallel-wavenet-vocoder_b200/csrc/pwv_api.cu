@@ -93,6 +93,7 @@ struct pwv_model {
   int last_launches = 0;
 
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
+  long long* trace = nullptr;    // pwv_debug_set_trace
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
   int ev_used = 0;
@@ -379,7 +380,18 @@ int pwv_model_finalize(pwv_model* m) {
           s.bd = arena.data() + lo.bd;
           src.push_back(s);
         }
-    const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src);
+    std::vector<pwv::TcPostSrc> posts;
+    for (int i = 0; i < hp.n_iaf; ++i)
+      for (int b = 0; b < 2; ++b) {
+        const BodyOff& bo = m->bodies[i * 2 + b];
+        const LayerOff& lo = bo.layers[hp.n_layers[i] - 1];
+        pwv::TcPostSrc q;
+        q.ws = arena.data() + lo.ws; q.bs = arena.data() + lo.bs;
+        q.w1 = arena.data() + bo.w1; q.b1 = arena.data() + bo.b1;
+        q.w2 = arena.data() + bo.w2; q.b2 = arena.data() + bo.b2;
+        posts.push_back(q);
+      }
+    const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src, posts);
     if (err) return fail(PWV_ECUDA, "tensor-core weight images: %s", err);
   }
   m->finalized = true;
@@ -496,7 +508,6 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
 static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st,
                             const pwv_taps* taps, int* cur_buf, int* launches) {
   constexpr int C = pwv::TC_C;
-  using Cfg = pwv::TileCfg<C>;
   const pwv_hparams& hp = m->hp;
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
   const bool bf16 = hp.precision == PWV_PREC_BF16;
@@ -505,7 +516,8 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
   if (!attr_set) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     attr_set = true;
   }
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
@@ -527,8 +539,9 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
     p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : 0;
     p.tiles_per_utt = tiles_per_utt;
+    p.trace = m->trace;
     PWV_PROF_MARK(m, st);
-    kern<<<grid, 288, pwv::TC_SMEM_BYTES, st>>>(p);
+    kern<<<grid, pwv::TC_THREADS, pwv::TC_SMEM_BYTES, st>>>(p);
     PWV_PROF_MARK(m, st);
     ++*launches;
     cur ^= 1;
@@ -536,18 +549,14 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
       PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * N * T * C,
                                sizeof(float) * (size_t)N * T * C, cudaMemcpyDeviceToDevice, st));
   }
-  pwv::PostParams q;
+  // post-net of both bodies on the tensor cores; the two channel halves of a row accumulate into y
+  PWV_CUDA(cudaMemsetAsync(w.ss, 0, sizeof(float) * 2 * (size_t)N * T, st));
+  pwv::TcPostParams q;
   q.z = w.act[cur];
-  for (int b = 0; b < 2; ++b) {
-    const BodyOff& bo = m->bodies[flow * 2 + b];
-    const LayerOff& lo = bo.layers[L - 1];
-    q.ws[b] = m->d_arena + lo.ws; q.bs[b] = m->d_arena + lo.bs;
-    q.w1[b] = m->d_arena + bo.w1; q.b1[b] = m->d_arena + bo.b1;
-    q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
-  }
-  q.y = w.ss; q.N = N; q.T = T;
-  dim3 pgrid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
-  pwv::k_post_simt<C><<<pgrid, Cfg::NT, Cfg::SMEM, st>>>(q);
+  for (int b = 0; b < 2; ++b) q.image[b] = m->tc.d_post + ((size_t)flow * 2 + b) * pwv::TCP_IMAGE_BYTES;
+  q.y = w.ss; q.N = N; q.T = T; q.tiles_per_utt = tiles_per_utt;
+  if (bf16) pwv::k_post_tc<true, false><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(q);
+  else pwv::k_post_tc<false, true><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(q);
   ++*launches;
   *cur_buf = cur;
   PWV_CUDA(cudaGetLastError());
@@ -674,6 +683,12 @@ int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* 
 }
 
 int pwv_last_launch_count(const pwv_model* m) { return m ? m->last_launches : fail(PWV_EINVAL, "null model"); }
+
+int pwv_debug_set_trace(pwv_model* m, long long* device_buffer) {
+  if (!m) return fail(PWV_EINVAL, "null model");
+  m->trace = device_buffer;
+  return PWV_OK;
+}
 
 int pwv_set_profiling(pwv_model* m, int enable) {
   if (!m) return fail(PWV_EINVAL, "null model");

@@ -22,11 +22,14 @@
 // K-major no-swizzle core-matrix layout, loaded once per CTA by 1-D bulk copies (TMA unit).
 // Activations move HBM -> shared -> HBM as 256-byte rows by per-thread bulk copies.
 //
-// Warp roles (288 threads): warps 0-3 and 4-7 are two worker groups, each owning a TMEM slot
-// (256 columns: D1 128 | A1hi 64 | A1lo 64; D2 and z alias D1 / A1) and a staging slot and
-// processing alternate tiles, so one group's epilogue overlaps the other group's MMAs; warp 8
-// allocates TMEM, loads weights and issues every MMA (one elected thread), dispatching
-// whichever group is ready.
+// Warp roles (544 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
+// A tile slot owns 256 TMEM columns (D1 128 | A1hi 64 | A1lo 64; D2 and z alias D1 / A1) and a
+// staging slot; the two slots hold alternate tiles, so one tile's epilogue overlaps the other
+// tile's MMAs. Within a slot a thread owns one row and 32 of its 64 channels (the two warps that
+// share a lane quarter split the columns), which doubles the warps available to hide the MUFU /
+// TMEM / mbarrier latencies of the epilogues. Warp 16 allocates TMEM, loads the weights and issues
+// every MMA (one elected thread), dispatching whichever slot is ready. The next tile's x[t-d]
+// rows are prefetched as soon as the current ones are converted.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -72,8 +75,34 @@ struct TcLayerSrc {
 
 struct TcModel {
   uint8_t* d_images = nullptr;   // [n_layers_total] x TC_IMAGE_BYTES, order = (flow, body, layer)
+  uint8_t* d_post = nullptr;     // [n_iaf * 2] x TCP_IMAGE_BYTES, order = (flow, body)
   size_t bytes = 0;
   int precision = 0;
+};
+
+// post-net image of one (flow, body): skip 1x1 (64 -> 128), postprocess1 (128 -> 128), vectors
+constexpr int TCP_WS_BYTES = 64 * 128 * 2;      // [k/8][n=128][8]
+constexpr int TCP_W1_BYTES = 128 * 128 * 2;
+constexpr int TCP_OFF_WSHI = 0;
+constexpr int TCP_OFF_WSLO = TCP_OFF_WSHI + TCP_WS_BYTES;
+constexpr int TCP_OFF_W1HI = TCP_OFF_WSLO + TCP_WS_BYTES;
+constexpr int TCP_OFF_W1LO = TCP_OFF_W1HI + TCP_W1_BYTES;
+constexpr int TCP_OFF_BS = TCP_OFF_W1LO + TCP_W1_BYTES;   // 128 floats: skip bias
+constexpr int TCP_OFF_B1 = TCP_OFF_BS + 512;              // 128 floats: postprocess1 bias
+constexpr int TCP_OFF_W2 = TCP_OFF_B1 + 512;              // 128 floats: postprocess2 weights
+constexpr int TCP_OFF_SCAL = TCP_OFF_W2 + 512;            // 1/s_skip, 1/s_1, b2
+constexpr int TCP_IMAGE_BYTES = TCP_OFF_SCAL + 256;       // 100,096
+constexpr int TCP_STAGE_BYTES = TC_TM * TC_ROW_PITCH;     // z rows of one tile slot
+constexpr int TCP_SMEM_STAGE0 = ((TCP_IMAGE_BYTES + 1023) / 1024) * 1024;
+constexpr int TCP_SMEM_BYTES = TCP_SMEM_STAGE0 + 2 * TCP_STAGE_BYTES + 256;
+
+struct TcPostSrc {
+  const float* ws;   // host [64][128]
+  const float* bs;   // [128]
+  const float* w1;   // [128][128]
+  const float* b1;   // [128]
+  const float* w2;   // [128]
+  const float* b2;   // [1]
 };
 
 inline uint16_t tc_to16(float v, bool bf16) {
@@ -111,12 +140,15 @@ inline void tc_pack_b(uint8_t* hi, uint8_t* lo, const float* w, int K, int Ncols
 
 inline void tc_model_free(TcModel& t) {
   if (t.d_images) cudaFree(t.d_images);
+  if (t.d_post) cudaFree(t.d_post);
   t.d_images = nullptr;
+  t.d_post = nullptr;
   t.bytes = 0;
 }
 
 // precision: 1 = f16x3, 2 = bf16. Returns nullptr on success or a static error string.
-inline const char* tc_model_build(TcModel& t, int precision, int C, const std::vector<TcLayerSrc>& layers) {
+inline const char* tc_model_build(TcModel& t, int precision, int C, const std::vector<TcLayerSrc>& layers,
+                                  const std::vector<TcPostSrc>& posts) {
   if (C != TC_C) return "tensor-core kernels need residual_channels = 64";
   const bool bf16 = precision == 2, split = precision == 1;
   std::vector<uint8_t> host(layers.size() * (size_t)TC_IMAGE_BYTES, 0);
@@ -133,7 +165,22 @@ inline const char* tc_model_build(TcModel& t, int precision, int C, const std::v
   tc_model_free(t);
   if (cudaMalloc(&t.d_images, host.size()) != cudaSuccess) return "cudaMalloc of the tensor-core weight images failed";
   if (cudaMemcpy(t.d_images, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) return "upload of the tensor-core weight images failed";
-  t.bytes = host.size();
+  std::vector<uint8_t> hpost(posts.size() * (size_t)TCP_IMAGE_BYTES, 0);
+  for (size_t i = 0; i < posts.size(); ++i) {
+    uint8_t* img = hpost.data() + i * (size_t)TCP_IMAGE_BYTES;
+    const float ss = bf16 ? 1.f : tc_pow2_scale(posts[i].ws, (size_t)64 * 128);
+    const float s1 = bf16 ? 1.f : tc_pow2_scale(posts[i].w1, (size_t)128 * 128);
+    tc_pack_b(img + TCP_OFF_WSHI, img + TCP_OFF_WSLO, posts[i].ws, 64, 128, ss, bf16, split);
+    tc_pack_b(img + TCP_OFF_W1HI, img + TCP_OFF_W1LO, posts[i].w1, 128, 128, s1, bf16, split);
+    std::memcpy(img + TCP_OFF_BS, posts[i].bs, 128 * sizeof(float));
+    std::memcpy(img + TCP_OFF_B1, posts[i].b1, 128 * sizeof(float));
+    std::memcpy(img + TCP_OFF_W2, posts[i].w2, 128 * sizeof(float));
+    const float scal[4] = {1.f / ss, 1.f / s1, posts[i].b2[0], 0.f};
+    std::memcpy(img + TCP_OFF_SCAL, scal, sizeof(scal));
+  }
+  if (cudaMalloc(&t.d_post, hpost.size()) != cudaSuccess) return "cudaMalloc of the post-net weight images failed";
+  if (cudaMemcpy(t.d_post, hpost.data(), hpost.size(), cudaMemcpyHostToDevice) != cudaSuccess) return "upload of the post-net weight images failed";
+  t.bytes = host.size() + hpost.size();
   t.precision = precision;
   return nullptr;
 }
@@ -148,7 +195,14 @@ struct TcLayerParams {
   const float* cbias[2];    // per body [N][t_mel][128], PRE-SCALED: filter half by KF, gate half by KG
   int N, T, t_mel, hop, dilation, mode;
   int tiles_per_utt;        // ceil(T / 128)
+  long long* trace;         // debug: [3 roles][16 tiles][16 events] clock64 stamps of CTA 0 (or nullptr)
 };
+
+// debug timeline of CTA 0: role 0/1 = first thread of tile slot 0/1, role 2 = the MMA-issuing thread
+#define TC_TRACE(role, j, k)                                                         \
+  do {                                                                               \
+    if (p.trace && blockIdx.x == 0 && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
+  } while (0)
 
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack16(float a, float b) {   // a -> low half (even k), b -> high half
@@ -197,12 +251,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // barrier block at the end of dynamic shared memory
 struct TcBarriers {
   uint64_t w_ready;
-  uint64_t load[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
+  uint64_t load_x[2], load_y[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
 };
 
+constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
+constexpr int TC_THREADS = (TC_WORKER_WARPS + 1) * 32;    // + control warp
+
 template <bool BF16, bool SPLIT>
-__global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* smem = tc_smem;
@@ -211,18 +268,19 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
   const int body = blockIdx.x & 1;
   const int cta_in_body = blockIdx.x >> 1, ctas_per_body = (gridDim.x + 1 - body) >> 1;
   const int tiles_body = p.N * p.tiles_per_utt;
-  // this CTA's tiles: cta_in_body, +ctas_per_body, ...; local index j; worker group g takes j % 2 == g
+  // this CTA's tiles: cta_in_body, +ctas_per_body, ...; local index; tile slot s takes local % 2 == s
   const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
 
-  if (warp == 8) {
+  if (warp == TC_WORKER_WARPS) {
     if (lane == 0) {
       mbar_init(&bars->w_ready, 1);
-      for (int g = 0; g < 2; ++g) {
-        mbar_init(&bars->load[g], 128);
-        mbar_init(&bars->a_ready[g], 128);
-        mbar_init(&bars->d1_ready[g], 1);
-        mbar_init(&bars->z_ready[g], 128);
-        mbar_init(&bars->d2_ready[g], 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars->load_x[s], 256);
+        mbar_init(&bars->load_y[s], 256);
+        mbar_init(&bars->a_ready[s], 256);
+        mbar_init(&bars->d1_ready[s], 1);
+        mbar_init(&bars->z_ready[s], 256);
+        mbar_init(&bars->d2_ready[s], 1);
       }
       fence_mbar_init();
     }
@@ -235,7 +293,7 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
   const uint32_t tmem = bars->tmem_base;
   const size_t body_off = (size_t)body * p.N * p.T * TC_C;
 
-  if (warp == 8) {
+  if (warp == TC_WORKER_WARPS) {
     // ======================= control warp: weights + MMA issue =======================
     if (elect_one()) {
       const uint8_t* img = p.image[body];
@@ -248,26 +306,24 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
       const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
       const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
       constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
-      // per group: next op = 2*j + phase (phase 0: GEMM1, 1: GEMM2)
+      // per slot: next op = 2*j + phase (phase 0: GEMM1, 1: GEMM2); mode 1 has GEMM1 only
       int next_op[2] = {0, 0};
       int n_ops[2];
-      for (int g = 0; g < 2; ++g) {
-        const int tiles_g = (n_local + 1 - g) / 2;
-        n_ops[g] = tiles_g * (p.mode == 1 ? 1 : 2);
-      }
-      int g = 0;
+      for (int s = 0; s < 2; ++s) n_ops[s] = ((n_local + 1 - s) / 2) * (p.mode == 1 ? 1 : 2);
+      int s = 0;
       while (next_op[0] < n_ops[0] || next_op[1] < n_ops[1]) {
-        if (next_op[g] < n_ops[g]) {
-          const int j = (p.mode == 1) ? next_op[g] : next_op[g] >> 1;
-          const int phase = (p.mode == 1) ? 0 : next_op[g] & 1;
-          uint64_t* ready = phase == 0 ? &bars->a_ready[g] : &bars->z_ready[g];
-          if (mbar_try_wait(ready, j & 1)) {
+        if (next_op[s] < n_ops[s]) {
+          const int j = (p.mode == 1) ? next_op[s] : next_op[s] >> 1;
+          const int phase = (p.mode == 1) ? 0 : next_op[s] & 1;
+          uint64_t* ready = phase == 0 ? &bars->a_ready[s] : &bars->z_ready[s];
+          if (mbar_test_wait(ready, j & 1)) {
             tc_fence_after_sync();
-            const uint32_t tD = tmem + g * 256;
-            const uint32_t tAhi = tmem + g * 256 + 128, tAlo = tmem + g * 256 + 192;
+            TC_TRACE(2, j, s * 8 + phase * 2);
+            const uint32_t tD = tmem + s * 256;
+            const uint32_t tAhi = tD + 128, tAlo = tD + 192;
             if (phase == 0) {
-              // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi   (K = 128: 8 steps of 16; a step = 8 TMEM columns,
-              // 2 K-chunks of 128 rows x 16 B in shared memory)
+              // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi   (K = 128: 8 steps of 16; a step = 8 TMEM columns
+              // of A and 2 K-chunks of 128 rows x 16 B of B)
               uint32_t acc = 0;
               if (SPLIT) {
 #pragma unroll
@@ -280,7 +336,7 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks, acc = 1)
                 mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-              mma_commit(&bars->d1_ready[g]);
+              mma_commit(&bars->d1_ready[s]);
             } else {
               // D2 = z.W2 (K = 64: 4 steps; chunk = 64 rows x 16 B)
               uint32_t acc = 0;
@@ -295,93 +351,121 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks, acc = 1)
                 mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-              mma_commit(&bars->d2_ready[g]);
+              mma_commit(&bars->d2_ready[s]);
             }
-            ++next_op[g];
+            TC_TRACE(2, j, s * 8 + phase * 2 + 1);
+            ++next_op[s];
           }
         }
-        g ^= 1;
+        s ^= 1;
       }
     }
     __syncwarp();
   } else {
-    // ======================= worker groups: loads, operand prep, epilogues, stores =======================
-    const int g = warp >> 2;                      // worker group = TMEM / staging slot
-    const int r = threadIdx.x & 127;              // row of the tile = TMEM lane
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tD = tmem + g * 256 + lane_base;
+    // ======================= workers: loads, operand prep, epilogues, stores =======================
+    // warp -> (tile slot, channel half, lane quarter); thread -> (row of the tile, 32 of the 64 channels)
+    const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tD = tmem + slot * 256 + lane_base;
     const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-    uint8_t* stage = smem + TC_SMEM_STAGE0 + g * TC_STAGE_BYTES;
-    uint8_t* row_d = stage + r * TC_ROW_PITCH;                          // x[t-d] row
-    uint8_t* row_c = stage + TC_TM * TC_ROW_PITCH + r * TC_ROW_PITCH;   // x[t] row, later the output row
-    const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD);
+    uint8_t* stage = smem + TC_SMEM_STAGE0 + slot * TC_STAGE_BYTES;
+    uint8_t* my_x = stage + r * TC_ROW_PITCH + half * 128;                          // x[t-d], my 32 channels
+    uint8_t* my_y = stage + TC_TM * TC_ROW_PITCH + r * TC_ROW_PITCH + half * 128;   // x[t]; later the output
+    const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + half * 32;
     const float* scal = reinterpret_cast<const float*>(smem + TC_OFF_SCAL);
+    uint64_t* bar_x = &bars->load_x[slot];
+    uint64_t* bar_y = &bars->load_y[slot];
+
+    // stage my half of row `r` of local tile `local` (x[t-d] -> my_x, x[t] -> my_y)
+    auto issue_x = [&](int local) {
+      const int tile = cta_in_body + local * ctas_per_body;
+      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
+      if (t < p.T && t - p.dilation >= 0) {
+        mbar_arrive_expect_tx(bar_x, 128);
+        bulk_g2s(my_x, p.x_in + body_off + ((size_t)n * p.T + t - p.dilation) * TC_C + half * 32, 128, bar_x);
+      } else {
+        mbar_arrive(bar_x);
+      }
+    };
+    auto issue_y = [&](int local) {
+      const int tile = cta_in_body + local * ctas_per_body;
+      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
+      if (t < p.T) {
+        mbar_arrive_expect_tx(bar_y, 128);
+        bulk_g2s(my_y, p.x_in + body_off + ((size_t)n * p.T + t) * TC_C + half * 32, 128, bar_y);
+      } else {
+        mbar_arrive(bar_y);
+      }
+    };
+    // 32 staged floats -> 16 packed hi columns (+ 16 lo) at TMEM column `col`
+    auto prep = [&](const uint8_t* src, bool ok, uint32_t col) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float v[8];
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+          if (ok) { a = s4[c * 4 + q * 2]; b = s4[c * 4 + q * 2 + 1]; }
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
+        }
+        tmem_st8(tAhi + col + c * 8, hi);
+        if (SPLIT) tmem_st8(tAlo + col + c * 8, lo);
+      }
+    };
+
+    if (slot < n_local) { issue_x(slot); issue_y(slot); }
     bool weights_seen = false;
     float sf = 0.f, sg = 0.f, s2 = 0.f;
 
     int j = 0;
-    for (int local = g; local < n_local; local += 2, ++j) {
+    for (int local = slot; local < n_local; local += 2, ++j) {
       const int tile = cta_in_body + local * ctas_per_body;
-      const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TC_TM;
-      const int t = t0 + r;
+      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
       const bool row_ok = t < p.T;
       const bool del_ok = row_ok && (t - p.dilation >= 0);
-      const float* xrow = p.x_in + body_off + ((size_t)n * p.T + t) * TC_C;
+      const bool more = local + 2 < n_local;
       const uint32_t par = j & 1;
 
-      // ---- stage the two input rows (bulk copies complete on load[g])
-      {
-        const uint32_t bytes = (row_ok ? 256u : 0u) + (del_ok ? 256u : 0u);
-        if (bytes) {
-          mbar_arrive_expect_tx(&bars->load[g], bytes);
-          if (row_ok) bulk_g2s(row_c, xrow, 256, &bars->load[g]);
-          if (del_ok) bulk_g2s(row_d, xrow - (size_t)p.dilation * TC_C, 256, &bars->load[g]);
-        } else {
-          mbar_arrive(&bars->load[g]);
-        }
+      const bool tracer = (warp & 7) == 0 && lane == 0;
+      // ---- operand prep: A1 = [x[t-d] | x[t]] -> fp16 hi/lo -> TMEM (k = channel, +64 for the t tap)
+      if (tracer) TC_TRACE(slot, j, 0);
+      mbar_wait(bar_x, par);
+      if (tracer) TC_TRACE(slot, j, 1);
+      prep(my_x, del_ok, half * 16);
+      if (more) {                       // my x[t-d] slot is free again: prefetch the next tile's
+        fence_proxy_async_smem();
+        issue_x(local + 2);
       }
-      mbar_wait(&bars->load[g], par);
-
-      // ---- operand prep: A1 = [x[t-d] | x[t]] -> fp16 hi/lo -> TMEM (2 elements per column)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float4* src = reinterpret_cast<const float4*>(half == 0 ? row_d : row_c);
-        const bool ok = half == 0 ? del_ok : row_ok;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {        // 16 floats -> 8 hi columns + 8 lo columns
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float v[8];
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (ok) { a = src[c * 4 + q * 2]; b = src[c * 4 + q * 2 + 1]; }
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
-          }
-          tmem_st8(tAhi + half * 32 + c * 8, hi);
-          if (SPLIT) tmem_st8(tAlo + half * 32 + c * 8, lo);
-        }
-      }
+      if (tracer) TC_TRACE(slot, j, 2);
+      mbar_wait(bar_y, par);
+      if (tracer) TC_TRACE(slot, j, 3);
+      prep(my_y, row_ok, 32 + half * 16);
       tmem_wait_st();
       tc_fence_before_sync();
-      mbar_arrive(&bars->a_ready[g]);
+      mbar_arrive(&bars->a_ready[slot]);
+      if (tracer) TC_TRACE(slot, j, 4);
 
-      if (!weights_seen) {            // scalars / bias live in the weight image
+      if (!weights_seen) {              // scalars / bias live in the weight image
         mbar_wait(&bars->w_ready, 0);
         sf = scal[0]; sg = scal[1]; s2 = scal[2];
         weights_seen = true;
       }
       const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
-      const float4* cb = reinterpret_cast<const float4*>(p.cbias[body] + ((size_t)n * p.t_mel + frame) * 128);
+      const float4* cb = reinterpret_cast<const float4*>(p.cbias[body] + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
 
-      // ---- epilogue 1: z = tanh(f) * sigmoid(g)
-      mbar_wait(&bars->d1_ready[g], par);
+      // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
+      mbar_wait(&bars->d1_ready[slot], par);
       tc_fence_after_sync();
+      if (tracer) TC_TRACE(slot, j, 5);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {          // 16 channels per step
+      for (int c = 0; c < 2; ++c) {
         uint32_t fr[16], gr[16];
-        tmem_ld16(tD + c * 16, fr);
-        tmem_ld16(tD + 64 + c * 16, gr);
+        tmem_ld16(tD + half * 32 + c * 16, fr);
+        tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
         float cf[16], cg[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -403,7 +487,7 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
           z[e] = (1.f - a) * rcp_approx((1.f + a) * (1.f + b));
         }
         if (p.mode == 1) {
-          float4* dst = reinterpret_cast<float4*>(row_c) + c * 4;   // x[t] row is dead in mode 1
+          float4* dst = reinterpret_cast<float4*>(my_y) + c * 4;   // x[t] is dead in mode 1
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
         } else {
@@ -413,23 +497,25 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
           for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
           split8<BF16, SPLIT>(v0, hi, lo);
           split8<BF16, SPLIT>(v1, hi + 4, lo + 4);
-          tmem_st8(tAhi + c * 8, hi);
-          if (SPLIT) tmem_st8(tAlo + c * 8, lo);
+          tmem_st8(tAhi + half * 16 + c * 8, hi);
+          if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
         }
       }
       if (p.mode != 1) {
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&bars->z_ready[g]);
+        mbar_arrive(&bars->z_ready[slot]);
+        if (tracer) TC_TRACE(slot, j, 6);
 
-        // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in the staged x[t] row)
-        mbar_wait(&bars->d2_ready[g], par);
+        // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] half row)
+        mbar_wait(&bars->d2_ready[slot], par);
         tc_fence_after_sync();
+        if (tracer) TC_TRACE(slot, j, 7);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t dr[16];
-          tmem_ld16(tD + c * 16, dr);
-          float4* xr = reinterpret_cast<float4*>(row_c) + c * 4;
+          tmem_ld16(tD + half * 32 + c * 16, dr);
+          float4* xr = reinterpret_cast<float4*>(my_y) + c * 4;
           float4 xv[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) xv[q] = xr[q];
@@ -446,20 +532,238 @@ __global__ void __launch_bounds__(288, 1) k_layer_tc(TcLayerParams p) {
           }
         }
       }
-      // ---- store the row (bulk copy from shared memory), then make the staging row reusable
+      // ---- store my half row (bulk copy from shared memory); once it has been read, refill it
       tc_fence_before_sync();
+      if (tracer) TC_TRACE(slot, j, 8);
       if (row_ok) {
         fence_proxy_async_smem();
-        bulk_s2g(p.x_out + body_off + ((size_t)n * p.T + t) * TC_C, row_c, 256);
+        bulk_s2g(p.x_out + body_off + ((size_t)n * p.T + t) * TC_C + half * 32, my_y, 128);
         bulk_commit();
         bulk_wait_read0();
       }
+      if (tracer) TC_TRACE(slot, j, 9);
+      if (more) issue_y(local + 2);
     }
     if (j > 0) bulk_wait0();
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Post-net of both bodies on the tensor cores (reference modules.py:145-165, use_skip_connection
+// False): per 128-row tile
+//   D [128 x 128] = z . Ws                     (the last layer's skip 1x1; z from k_layer_tc mode 1)
+//   h             = relu(D + bs)          -> A operand of the next GEMM (fp16 hi/lo in TMEM)
+//   D'[128 x 128] = h . W1                     (postprocess1)
+//   y             = relu(D' + b1) . w2 + b2    (postprocess2: 128 -> 1, in-thread dot product; the two
+//                                               column halves of a row meet in one atomicAdd each on a
+//                                               zeroed output -- two addends, so the sum is order-free)
+// Same roles, TMEM slots and staging scheme as k_layer_tc.
+// ------------------------------------------------------------------------------------------------
+struct TcPostParams {
+  const float* z;           // [2][N][T][64]
+  const uint8_t* image[2];
+  float* y;                 // [2][N][T], zeroed before the launch
+  int N, T, tiles_per_utt;
+};
+
+struct TcPostBarriers {
+  uint64_t w_ready;
+  uint64_t load_z[2], a_ready[2], ds_ready[2], h_ready[2], d1_ready[2];
+  uint32_t tmem_base;
+};
+
+template <bool BF16, bool SPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
+  using namespace ptx;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* smem = tc_smem;
+  TcPostBarriers* bars = reinterpret_cast<TcPostBarriers*>(smem + TCP_SMEM_STAGE0 + 2 * TCP_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int body = blockIdx.x & 1;
+  const int cta_in_body = blockIdx.x >> 1, ctas_per_body = (gridDim.x + 1 - body) >> 1;
+  const int tiles_body = p.N * p.tiles_per_utt;
+  const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
+
+  if (warp == TC_WORKER_WARPS) {
+    if (lane == 0) {
+      mbar_init(&bars->w_ready, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars->load_z[s], 256);
+        mbar_init(&bars->a_ready[s], 256);
+        mbar_init(&bars->ds_ready[s], 1);
+        mbar_init(&bars->h_ready[s], 256);
+        mbar_init(&bars->d1_ready[s], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+  const size_t body_off = (size_t)body * p.N * p.T;
+
+  if (warp == TC_WORKER_WARPS) {
+    if (elect_one()) {
+      const uint8_t* img = p.image[body];
+      mbar_arrive_expect_tx(&bars->w_ready, TCP_IMAGE_BYTES);
+      for (int off = 0; off < TCP_IMAGE_BYTES; off += 16384) {
+        const int n = min(16384, TCP_IMAGE_BYTES - off);
+        bulk_g2s(smem + off, img + off, n, &bars->w_ready);
+      }
+      mbar_wait(&bars->w_ready, 0);
+      const uint32_t wshi = smem_u32(smem + TCP_OFF_WSHI), wslo = smem_u32(smem + TCP_OFF_WSLO);
+      const uint32_t w1hi = smem_u32(smem + TCP_OFF_W1HI), w1lo = smem_u32(smem + TCP_OFF_W1LO);
+      constexpr uint32_t ID = idesc_f16(128, 128, BF16);
+      int next_op[2] = {0, 0};
+      int n_ops[2];
+      for (int s = 0; s < 2; ++s) n_ops[s] = ((n_local + 1 - s) / 2) * 2;
+      int s = 0;
+      while (next_op[0] < n_ops[0] || next_op[1] < n_ops[1]) {
+        if (next_op[s] < n_ops[s]) {
+          const int j = next_op[s] >> 1, phase = next_op[s] & 1;
+          uint64_t* ready = phase == 0 ? &bars->a_ready[s] : &bars->h_ready[s];
+          if (mbar_test_wait(ready, j & 1)) {
+            tc_fence_after_sync();
+            const uint32_t tD = tmem + s * 256;
+            const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+            const int ksteps = phase == 0 ? 4 : 8;          // K = 64 (z) / 128 (h)
+            const uint32_t bhi = phase == 0 ? wshi : w1hi, blo = phase == 0 ? wslo : w1lo;
+            uint32_t acc = 0;
+            if (SPLIT) {
+              for (int ks = 0; ks < ksteps; ++ks, acc = 1)
+                mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
+              for (int ks = 0; ks < ksteps; ++ks)
+                mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(blo + ks * 2 * 2048, 2048, 128), ID, 1);
+            }
+            for (int ks = 0; ks < ksteps; ++ks, acc = 1)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
+            mma_commit(phase == 0 ? &bars->ds_ready[s] : &bars->d1_ready[s]);
+            ++next_op[s];
+          }
+        }
+        s ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tD = tmem + slot * 256 + lane_base;
+    const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+    uint8_t* my_z = smem + TCP_SMEM_STAGE0 + slot * TCP_STAGE_BYTES + r * TC_ROW_PITCH + half * 128;
+    const float* bs_s = reinterpret_cast<const float*>(smem + TCP_OFF_BS) + half * 64;
+    const float* b1_s = reinterpret_cast<const float*>(smem + TCP_OFF_B1) + half * 64;
+    const float* w2_s = reinterpret_cast<const float*>(smem + TCP_OFF_W2) + half * 64;
+    const float* scal = reinterpret_cast<const float*>(smem + TCP_OFF_SCAL);
+    uint64_t* bar_z = &bars->load_z[slot];
+
+    auto issue_z = [&](int local) {
+      const int tile = cta_in_body + local * ctas_per_body;
+      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
+      if (t < p.T) {
+        mbar_arrive_expect_tx(bar_z, 128);
+        bulk_g2s(my_z, p.z + (body_off + (size_t)n * p.T + t) * TC_C + half * 32, 128, bar_z);
+      } else {
+        mbar_arrive(bar_z);
+      }
+    };
+    if (slot < n_local) issue_z(slot);
+    bool weights_seen = false;
+    float ss = 0.f, s1 = 0.f, b2 = 0.f;
+
+    int j = 0;
+    for (int local = slot; local < n_local; local += 2, ++j) {
+      const int tile = cta_in_body + local * ctas_per_body;
+      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
+      const bool row_ok = t < p.T;
+      const uint32_t par = j & 1;
+
+      // ---- A = z (my 32 channels: k = 32*half ..) -> fp16 hi/lo -> TMEM columns 16*half ..
+      mbar_wait(bar_z, par);
+      {
+        const float4* s4 = reinterpret_cast<const float4*>(my_z);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float v[8];
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (row_ok) { a = s4[c * 4 + q * 2]; b = s4[c * 4 + q * 2 + 1]; }
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
+          }
+          tmem_st8(tAhi + half * 16 + c * 8, hi);
+          if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+        }
+      }
+      if (local + 2 < n_local) {
+        fence_proxy_async_smem();
+        issue_z(local + 2);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->a_ready[slot]);
+
+      if (!weights_seen) {
+        mbar_wait(&bars->w_ready, 0);
+        ss = scal[0]; s1 = scal[1]; b2 = scal[2];
+        weights_seen = true;
+      }
+
+      // ---- h = relu(skip) on my 64 of the 128 columns -> A' (k = 64*half .., columns 32*half ..)
+      mbar_wait(&bars->ds_ready[slot], par);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t dr[16];
+        tmem_ld16(tD + half * 64 + c * 16, dr);
+        tmem_wait_ld();
+        float v0[8], v1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v0[e] = fmaxf(fmaf(__uint_as_float(dr[e]), ss, bs_s[c * 16 + e]), 0.f);
+          v1[e] = fmaxf(fmaf(__uint_as_float(dr[8 + e]), ss, bs_s[c * 16 + 8 + e]), 0.f);
+        }
+        uint32_t hi[8], lo[8];
+        split8<BF16, SPLIT>(v0, hi, lo);
+        split8<BF16, SPLIT>(v1, hi + 4, lo + 4);
+        // all 256 threads of the slot have to finish READING D before anyone overwrites A? No: A'
+        // occupies the A columns (128..255 of the slot), D the first 128 -- disjoint.
+        tmem_st8(tAhi + half * 32 + c * 8, hi);
+        if (SPLIT) tmem_st8(tAlo + half * 32 + c * 8, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->h_ready[slot]);
+
+      // ---- y = relu(D' + b1) . w2 (+ b2 once per row)
+      mbar_wait(&bars->d1_ready[slot], par);
+      tc_fence_after_sync();
+      float acc = half == 0 ? b2 : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t dr[16];
+        tmem_ld16(tD + half * 64 + c * 16, dr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          acc = fmaf(fmaxf(fmaf(__uint_as_float(dr[e]), s1, b1_s[c * 16 + e]), 0.f), w2_s[c * 16 + e], acc);
+      }
+      tc_fence_before_sync();
+      if (row_ok) atomicAdd(p.y + body_off + (size_t)n * p.T + t, acc);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pwv
