@@ -3,6 +3,7 @@
 // (reference models.py:23-78 -> modules.py:53-60 -> modules.py:129-166).
 #include "../../include/pwv.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -504,8 +505,33 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
 }
 
 
-// gated layers of one flow on the tensor cores; the post-net stays on the fp32 kernel
-static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st,
+// 3-D TMA map of an activation buffer [2N utterance-bodies][T][64] fp32, box = 32 channels x 128
+// rows x 1, 128B swizzle, zero OOB fill (rows before/after an utterance read as zeros and are not
+// written). cuTensorMapEncodeTiled is fetched through the runtime so libcuda is not a link dependency.
+static int encode_act_map(CUtensorMap* map, float* base, int N, int T) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PWV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PWV_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)2 * N};
+  const cuuint64_t strides[2] = {64 * sizeof(float), (cuuint64_t)T * 64 * sizeof(float)};
+  const cuuint32_t box[3] = {32, (cuuint32_t)pwv::TC_TM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PWV_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (N=%d, T=%d)", (int)r, N, T);
+  return PWV_OK;
+}
+
+// gated layers and post-net of one flow on the tensor cores
+static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap* maps, int flow, int N, int T, cudaStream_t st,
                             const pwv_taps* taps, int* cur_buf, int* launches) {
   constexpr int C = pwv::TC_C;
   const pwv_hparams& hp = m->hp;
@@ -530,8 +556,6 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
   int cur = *cur_buf;
   for (int j = 0; j < L; ++j) {
     pwv::TcLayerParams p;
-    p.x_in = w.act[cur];
-    p.x_out = w.act[cur ^ 1];
     for (int b = 0; b < 2; ++b) {
       p.image[b] = m->tc.d_images + (layer_base + (size_t)b * L + j) * pwv::TC_IMAGE_BYTES;
       p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
@@ -541,7 +565,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
     p.tiles_per_utt = tiles_per_utt;
     p.trace = m->trace;
     PWV_PROF_MARK(m, st);
-    kern<<<grid, pwv::TC_THREADS, pwv::TC_SMEM_BYTES, st>>>(p);
+    kern<<<grid, pwv::TC_THREADS, pwv::TC_SMEM_BYTES, st>>>(maps[cur], maps[cur ^ 1], p);
     PWV_PROF_MARK(m, st);
     ++*launches;
     cur ^= 1;
@@ -552,11 +576,10 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, int flow, int N, i
   // post-net of both bodies on the tensor cores; the two channel halves of a row accumulate into y
   PWV_CUDA(cudaMemsetAsync(w.ss, 0, sizeof(float) * 2 * (size_t)N * T, st));
   pwv::TcPostParams q;
-  q.z = w.act[cur];
   for (int b = 0; b < 2; ++b) q.image[b] = m->tc.d_post + ((size_t)flow * 2 + b) * pwv::TCP_IMAGE_BYTES;
   q.y = w.ss; q.N = N; q.T = T; q.tiles_per_utt = tiles_per_utt;
-  if (bf16) pwv::k_post_tc<true, false><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(q);
-  else pwv::k_post_tc<false, true><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(q);
+  if (bf16) pwv::k_post_tc<true, false><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(maps[cur], q);
+  else pwv::k_post_tc<false, true><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(maps[cur], q);
   ++*launches;
   *cur_buf = cur;
   PWV_CUDA(cudaGetLastError());
@@ -590,6 +613,14 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     dim3 grid((Cc + 63) / 64, (M + 63) / 64, 1);
     pwv::k_row_gemm<true><<<grid, 256, 0, st>>>(mel, rb, M, hp.n_mels, Cc);
     ++launches;
+  }
+
+  CUtensorMap maps[2];
+  if (hp.precision != PWV_PREC_FP32) {
+    for (int b = 0; b < 2; ++b) {
+      rc = encode_act_map(&maps[b], w.act[b], N, T);
+      if (rc) return rc;
+    }
   }
 
   int cur = 0, xcur = 0;
@@ -628,7 +659,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
     } else {
-      rc = launch_layers_tc(m, w, i, N, T, st, taps, &cur, &launches);
+      rc = launch_layers_tc(m, w, maps, i, N, T, st, taps, &cur, &launches);
     }
     if (rc) return rc;
     if (taps && taps->scale_shift)

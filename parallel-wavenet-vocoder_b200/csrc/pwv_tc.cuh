@@ -20,19 +20,25 @@
 // Operand placement: A operands (activations, z) live in TMEM (written by the epilogue threads
 // with tcgen05.st, two 16-bit elements per column), B operands (weights) in shared memory in the
 // K-major no-swizzle core-matrix layout, loaded once per CTA by 1-D bulk copies (TMA unit).
-// Activations move HBM -> shared -> HBM as 256-byte rows by per-thread bulk copies.
+// Activations move HBM <-> shared memory as TMA tensor boxes (128 rows x 32 channels, 128B swizzle)
+// of a 3-D map [2N utterance-bodies][T][64]: rows before an utterance's start or past its end are
+// zero-filled on load and dropped on store by the TMA unit, so the causal zero history and ragged
+// last tiles need no masks. (Round-1 measurement that forced this: per-row 128/256-byte bulk copies
+// cost ~12 cycles of TMA issue each -- 9k cycles per tile, profiles/r1_tc_trace_v3_bulk_rows.txt.)
 //
-// Warp roles (544 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
+// Warp roles (576 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
 // A tile slot owns 256 TMEM columns (D1 128 | A1hi 64 | A1lo 64; D2 and z alias D1 / A1) and a
 // staging slot; the two slots hold alternate tiles, so one tile's epilogue overlaps the other
 // tile's MMAs. Within a slot a thread owns one row and 32 of its 64 channels (the two warps that
 // share a lane quarter split the columns), which doubles the warps available to hide the MUFU /
 // TMEM / mbarrier latencies of the epilogues. Warp 16 allocates TMEM, loads the weights and issues
-// every MMA (one elected thread), dispatching whichever slot is ready. The next tile's x[t-d]
-// rows are prefetched as soon as the current ones are converted.
+// every MMA (one elected thread), dispatching whichever slot is ready. Warp 17 is the TMA
+// producer: it refills a slot's x[t-d] boxes as soon as the workers have converted them, stores a
+// slot's output boxes when the workers have written them, then refills the x[t] boxes.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -62,8 +68,10 @@ constexpr int TC_IMAGE_BYTES = TC_OFF_SCAL + 256;         // 82,432 (multiple of
 constexpr float TC_KF = -2.8853900817779268f;  // -2*log2(e): a = 2^(KF*f) = e^(-2f)
 constexpr float TC_KG = -1.4426950408889634f;  // -log2(e):   b = 2^(KG*g) = e^(-g)
 
-constexpr int TC_ROW_PITCH = 272;              // staged 256-byte row + 16 bytes (bank spread)
-constexpr int TC_STAGE_BYTES = 2 * TC_TM * TC_ROW_PITCH;  // x[t-d] rows then x[t] rows
+// Staging of one tile slot: four TMA boxes of 128 rows x 32 channels (128 B rows, 128B-swizzled):
+// x[t-d] channels 0-31 | x[t-d] channels 32-63 | x[t] channels 0-31 | x[t] channels 32-63
+constexpr int TC_BOX_BYTES = TC_TM * 128;                 // 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_BOX_BYTES;          // 64 KB
 constexpr int TC_SMEM_STAGE0 = ((TC_IMAGE_BYTES + 1023) / 1024) * 1024;
 constexpr int TC_SMEM_BYTES = TC_SMEM_STAGE0 + 2 * TC_STAGE_BYTES + 256;   // + barriers / tmem slot
 
@@ -92,7 +100,7 @@ constexpr int TCP_OFF_B1 = TCP_OFF_BS + 512;              // 128 floats: postpro
 constexpr int TCP_OFF_W2 = TCP_OFF_B1 + 512;              // 128 floats: postprocess2 weights
 constexpr int TCP_OFF_SCAL = TCP_OFF_W2 + 512;            // 1/s_skip, 1/s_1, b2
 constexpr int TCP_IMAGE_BYTES = TCP_OFF_SCAL + 256;       // 100,096
-constexpr int TCP_STAGE_BYTES = TC_TM * TC_ROW_PITCH;     // z rows of one tile slot
+constexpr int TCP_STAGE_BYTES = 2 * TC_BOX_BYTES;         // z rows of one tile slot (two channel-half boxes)
 constexpr int TCP_SMEM_STAGE0 = ((TCP_IMAGE_BYTES + 1023) / 1024) * 1024;
 constexpr int TCP_SMEM_BYTES = TCP_SMEM_STAGE0 + 2 * TCP_STAGE_BYTES + 256;
 
@@ -189,16 +197,14 @@ inline const char* tc_model_build(TcModel& t, int precision, int C, const std::v
 // device side
 // ------------------------------------------------------------------------------------------------
 struct TcLayerParams {
-  const float* x_in;        // [2][N][T][64]
-  float* x_out;             // [2][N][T][64]  (mode 1: z of the last layer)
   const uint8_t* image[2];  // per body
   const float* cbias[2];    // per body [N][t_mel][128], PRE-SCALED: filter half by KF, gate half by KG
   int N, T, t_mel, hop, dilation, mode;
   int tiles_per_utt;        // ceil(T / 128)
-  long long* trace;         // debug: [3 roles][16 tiles][16 events] clock64 stamps of CTA 0 (or nullptr)
+  long long* trace;         // debug: [4 roles][16 tiles][16 events] clock64 stamps of CTA 0 (or nullptr)
 };
 
-// debug timeline of CTA 0: role 0/1 = first thread of tile slot 0/1, role 2 = the MMA-issuing thread
+// debug timeline of CTA 0: role 0/1 = first thread of tile slot 0/1, role 2 = MMA thread, 3 = producer
 #define TC_TRACE(role, j, k)                                                         \
   do {                                                                               \
     if (p.trace && blockIdx.x == 0 && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
@@ -248,18 +254,43 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// Logical 16-byte chunk `c` (0..7) of row `r` of a 128B-swizzled TMA box (rows are 128 B)
+__device__ __forceinline__ float4* box_chunk(uint8_t* box_row, int r, int c) {
+  return reinterpret_cast<float4*>(box_row + (((c ^ r) & 7) << 4));
+}
+
+// 32 staged floats of my box row -> 16 packed hi columns (+ 16 lo) at TMEM column taddr_hi / taddr_lo
+template <bool BF16, bool SPLIT>
+__device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_hi, uint32_t taddr_lo) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 a = *box_chunk(box_row, r, c * 4 + q * 2), b = *box_chunk(box_row, r, c * 4 + q * 2 + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
+    }
+    ptx::tmem_st8(taddr_hi + c * 8, hi);
+    if (SPLIT) ptx::tmem_st8(taddr_lo + c * 8, lo);
+  }
+}
+
+constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
+constexpr int TC_MMA_WARP = 16;
+constexpr int TC_TMA_WARP = 17;
+constexpr int TC_THREADS = (TC_WORKER_WARPS + 2) * 32;
+
 // barrier block at the end of dynamic shared memory
 struct TcBarriers {
   uint64_t w_ready;
-  uint64_t load_x[2], load_y[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
+  uint64_t x_full[2], y_full[2], x_free[2], out_ready[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
 };
 
-constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
-constexpr int TC_THREADS = (TC_WORKER_WARPS + 1) * 32;    // + control warp
-
 template <bool BF16, bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, TcLayerParams p) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* smem = tc_smem;
@@ -271,12 +302,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
   // this CTA's tiles: cta_in_body, +ctas_per_body, ...; local index; tile slot s takes local % 2 == s
   const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
 
-  if (warp == TC_WORKER_WARPS) {
+  if (warp == TC_MMA_WARP) {
     if (lane == 0) {
       mbar_init(&bars->w_ready, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&bars->load_x[s], 256);
-        mbar_init(&bars->load_y[s], 256);
+        mbar_init(&bars->x_full[s], 1);
+        mbar_init(&bars->y_full[s], 1);
+        mbar_init(&bars->x_free[s], 256);
+        mbar_init(&bars->out_ready[s], 256);
         mbar_init(&bars->a_ready[s], 256);
         mbar_init(&bars->d1_ready[s], 1);
         mbar_init(&bars->z_ready[s], 256);
@@ -291,12 +324,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
-  const size_t body_off = (size_t)body * p.N * p.T * TC_C;
 
-  if (warp == TC_WORKER_WARPS) {
-    // ======================= control warp: weights + MMA issue =======================
+  if (warp == TC_MMA_WARP) {
+    // ======================= weights + MMA issue =======================
     if (elect_one()) {
-      const uint8_t* img = p.image[body];
+      const uint8_t* img = body ? p.image[1] : p.image[0];
       mbar_arrive_expect_tx(&bars->w_ready, TC_IMAGE_BYTES);
       for (int off = 0; off < TC_IMAGE_BYTES; off += 16384) {
         const int n = min(16384, TC_IMAGE_BYTES - off);
@@ -361,8 +393,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
       }
     }
     __syncwarp();
+  } else if (warp == TC_TMA_WARP) {
+    // ======================= TMA producer: activation boxes in, output boxes out =======================
+    if (elect_one()) {
+      tma_prefetch_desc(&map_in);
+      tma_prefetch_desc(&map_out);
+      auto coords = [&](int local, int& ub, int& t0) {
+        const int tile = cta_in_body + local * ctas_per_body;
+        ub = body * p.N + tile / p.tiles_per_utt;          // utterance-body index (outermost map dim)
+        t0 = (tile % p.tiles_per_utt) * TC_TM;
+      };
+      auto issue_x = [&](int s, int local) {
+        int ub, t0;
+        coords(local, ub, t0);
+        uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+        mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st, &map_in, 0, t0 - p.dilation, ub, &bars->x_full[s]);
+        tma_load_3d(st + TC_BOX_BYTES, &map_in, 32, t0 - p.dilation, ub, &bars->x_full[s]);
+      };
+      auto issue_y = [&](int s, int local) {
+        int ub, t0;
+        coords(local, ub, t0);
+        uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES + 2 * TC_BOX_BYTES;
+        mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st, &map_in, 0, t0, ub, &bars->y_full[s]);
+        tma_load_3d(st + TC_BOX_BYTES, &map_in, 32, t0, ub, &bars->y_full[s]);
+      };
+      int tiles_s[2], jx[2] = {0, 0}, jo[2] = {0, 0};
+      for (int s = 0; s < 2; ++s) {
+        tiles_s[s] = (n_local + 1 - s) / 2;
+        if (tiles_s[s] > 0) { issue_x(s, s); issue_y(s, s); }
+      }
+      int s = 0;
+      while (jx[0] < tiles_s[0] || jo[0] < tiles_s[0] || jx[1] < tiles_s[1] || jo[1] < tiles_s[1]) {
+        if (jx[s] < tiles_s[s] && mbar_test_wait(&bars->x_free[s], jx[s] & 1)) {
+          // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile
+          if (jx[s] + 1 < tiles_s[s]) issue_x(s, s + 2 * (jx[s] + 1));
+          TC_TRACE(3, jx[s], s * 8 + 0);
+          ++jx[s];
+        }
+        if (jo[s] < tiles_s[s] && mbar_test_wait(&bars->out_ready[s], jo[s] & 1)) {
+          // the slot's x[t] boxes now hold the tile's output: store, then refill for the next tile
+          int ub, t0;
+          coords(s + 2 * jo[s], ub, t0);
+          uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES + 2 * TC_BOX_BYTES;
+          tma_store_3d(&map_out, 0, t0, ub, st);
+          tma_store_3d(&map_out, 32, t0, ub, st + TC_BOX_BYTES);
+          bulk_commit();
+          TC_TRACE(3, jo[s], s * 8 + 1);
+          if (jo[s] + 1 < tiles_s[s]) {
+            bulk_wait_read0();
+            issue_y(s, s + 2 * (jo[s] + 1));
+          }
+          TC_TRACE(3, jo[s], s * 8 + 2);
+          ++jo[s];
+        }
+        s ^= 1;
+      }
+      bulk_wait0();
+    }
+    __syncwarp();
   } else {
-    // ======================= workers: loads, operand prep, epilogues, stores =======================
+    // ======================= workers: operand prep, epilogues =======================
     // warp -> (tile slot, channel half, lane quarter); thread -> (row of the tile, 32 of the 64 channels)
     const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -370,54 +462,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
     const uint32_t tD = tmem + slot * 256 + lane_base;
     const uint32_t tAhi = tD + 128, tAlo = tD + 192;
     uint8_t* stage = smem + TC_SMEM_STAGE0 + slot * TC_STAGE_BYTES;
-    uint8_t* my_x = stage + r * TC_ROW_PITCH + half * 128;                          // x[t-d], my 32 channels
-    uint8_t* my_y = stage + TC_TM * TC_ROW_PITCH + r * TC_ROW_PITCH + half * 128;   // x[t]; later the output
+    uint8_t* my_x = stage + half * TC_BOX_BYTES + r * 128;                       // x[t-d], my 32 channels
+    uint8_t* my_y = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;    // x[t]; later the output
     const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + half * 32;
     const float* scal = reinterpret_cast<const float*>(smem + TC_OFF_SCAL);
-    uint64_t* bar_x = &bars->load_x[slot];
-    uint64_t* bar_y = &bars->load_y[slot];
-
-    // stage my half of row `r` of local tile `local` (x[t-d] -> my_x, x[t] -> my_y)
-    auto issue_x = [&](int local) {
-      const int tile = cta_in_body + local * ctas_per_body;
-      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
-      if (t < p.T && t - p.dilation >= 0) {
-        mbar_arrive_expect_tx(bar_x, 128);
-        bulk_g2s(my_x, p.x_in + body_off + ((size_t)n * p.T + t - p.dilation) * TC_C + half * 32, 128, bar_x);
-      } else {
-        mbar_arrive(bar_x);
-      }
-    };
-    auto issue_y = [&](int local) {
-      const int tile = cta_in_body + local * ctas_per_body;
-      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
-      if (t < p.T) {
-        mbar_arrive_expect_tx(bar_y, 128);
-        bulk_g2s(my_y, p.x_in + body_off + ((size_t)n * p.T + t) * TC_C + half * 32, 128, bar_y);
-      } else {
-        mbar_arrive(bar_y);
-      }
-    };
-    // 32 staged floats -> 16 packed hi columns (+ 16 lo) at TMEM column `col`
-    auto prep = [&](const uint8_t* src, bool ok, uint32_t col) {
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float v[8];
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (ok) { a = s4[c * 4 + q * 2]; b = s4[c * 4 + q * 2 + 1]; }
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
-        }
-        tmem_st8(tAhi + col + c * 8, hi);
-        if (SPLIT) tmem_st8(tAlo + col + c * 8, lo);
-      }
-    };
-
-    if (slot < n_local) { issue_x(slot); issue_y(slot); }
+    const bool tracer = (warp & 7) == 0 && lane == 0;
     bool weights_seen = false;
     float sf = 0.f, sg = 0.f, s2 = 0.f;
 
@@ -425,25 +474,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
     for (int local = slot; local < n_local; local += 2, ++j) {
       const int tile = cta_in_body + local * ctas_per_body;
       const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
-      const bool row_ok = t < p.T;
-      const bool del_ok = row_ok && (t - p.dilation >= 0);
-      const bool more = local + 2 < n_local;
       const uint32_t par = j & 1;
 
-      const bool tracer = (warp & 7) == 0 && lane == 0;
       // ---- operand prep: A1 = [x[t-d] | x[t]] -> fp16 hi/lo -> TMEM (k = channel, +64 for the t tap)
       if (tracer) TC_TRACE(slot, j, 0);
-      mbar_wait(bar_x, par);
+      mbar_wait(&bars->x_full[slot], par);
       if (tracer) TC_TRACE(slot, j, 1);
-      prep(my_x, del_ok, half * 16);
-      if (more) {                       // my x[t-d] slot is free again: prefetch the next tile's
-        fence_proxy_async_smem();
-        issue_x(local + 2);
-      }
+      tc_prep<BF16, SPLIT>(my_x, r, tAhi + half * 16, tAlo + half * 16);
+      mbar_arrive(&bars->x_free[slot]);          // (release: my reads of the boxes are done)
       if (tracer) TC_TRACE(slot, j, 2);
-      mbar_wait(bar_y, par);
+      mbar_wait(&bars->y_full[slot], par);
       if (tracer) TC_TRACE(slot, j, 3);
-      prep(my_y, row_ok, 32 + half * 16);
+      tc_prep<BF16, SPLIT>(my_y, r, tAhi + 32 + half * 16, tAlo + 32 + half * 16);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->a_ready[slot]);
@@ -455,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
         weights_seen = true;
       }
       const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
-      const float4* cb = reinterpret_cast<const float4*>(p.cbias[body] + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
+      const float4* cb = reinterpret_cast<const float4*>((body ? p.cbias[1] : p.cbias[0]) + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
 
       // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
       mbar_wait(&bars->d1_ready[slot], par);
@@ -477,19 +519,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
         float z[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          // fe = -2 log2e * f, ge = -log2e * g (cbias is pre-scaled); clamps keep a, b finite and the
-          // result within 1 ulp of saturation: tanh(10) = 1 - 4e-9, sigmoid(-18) = 1.5e-8
-          float fe = fmaf(__uint_as_float(fr[e]), sf, cf[e]);
-          float ge = fmaf(__uint_as_float(gr[e]), sg, cg[e]);
-          fe = fminf(fmaxf(fe, -28.853901f), 28.853901f);
-          ge = fminf(fmaxf(ge, -25.968511f), 25.968511f);
+          // fe = -2 log2e * f, ge = -log2e * g (cbias is pre-scaled)
+          // Only a = e^(-2f) needs an upper clamp: with a finite, b = inf gives rcp(inf) = 0 -> z = 0
+          // (the sigmoid -> 0 limit) and a, b -> 0 give z -> 1 * 1; 2^28.85: tanh = -1 + 4e-9.
+          const float fe = fminf(fmaf(__uint_as_float(fr[e]), sf, cf[e]), 28.853901f);
+          const float ge = fmaf(__uint_as_float(gr[e]), sg, cg[e]);
           const float a = ex2_approx(fe), b = ex2_approx(ge);
           z[e] = (1.f - a) * rcp_approx((1.f + a) * (1.f + b));
         }
-        if (p.mode == 1) {
-          float4* dst = reinterpret_cast<float4*>(my_y) + c * 4;   // x[t] is dead in mode 1
+        if (p.mode == 1) {              // last layer: z itself is the output (x[t] is dead)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
         } else {
           uint32_t hi[8], lo[8];
           float v0[8], v1[8];
@@ -515,10 +555,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
         for (int c = 0; c < 2; ++c) {
           uint32_t dr[16];
           tmem_ld16(tD + half * 32 + c * 16, dr);
-          float4* xr = reinterpret_cast<float4*>(my_y) + c * 4;
           float4 xv[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xv[q] = xr[q];
+          for (int q = 0; q < 4; ++q) xv[q] = *box_chunk(my_y, r, c * 4 + q);
           tmem_wait_ld();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -528,27 +567,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
             o.y = xv[q].y + fmaf(__uint_as_float(dr[4 * q + 1]), s2, b.y);
             o.z = xv[q].z + fmaf(__uint_as_float(dr[4 * q + 2]), s2, b.z);
             o.w = xv[q].w + fmaf(__uint_as_float(dr[4 * q + 3]), s2, b.w);
-            xr[q] = o;
+            *box_chunk(my_y, r, c * 4 + q) = o;
           }
         }
       }
-      // ---- store my half row (bulk copy from shared memory); once it has been read, refill it
+      // ---- hand the output boxes to the producer (generic writes -> async proxy)
       tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->out_ready[slot]);
       if (tracer) TC_TRACE(slot, j, 8);
-      if (row_ok) {
-        fence_proxy_async_smem();
-        bulk_s2g(p.x_out + body_off + ((size_t)n * p.T + t) * TC_C + half * 32, my_y, 128);
-        bulk_commit();
-        bulk_wait_read0();
-      }
-      if (tracer) TC_TRACE(slot, j, 9);
-      if (more) issue_y(local + 2);
     }
-    if (j > 0) bulk_wait0();
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem, 512);
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -563,7 +595,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_layer_tc(TcLayerParams p) {
 // Same roles, TMEM slots and staging scheme as k_layer_tc.
 // ------------------------------------------------------------------------------------------------
 struct TcPostParams {
-  const float* z;           // [2][N][T][64]
   const uint8_t* image[2];
   float* y;                 // [2][N][T], zeroed before the launch
   int N, T, tiles_per_utt;
@@ -571,12 +602,12 @@ struct TcPostParams {
 
 struct TcPostBarriers {
   uint64_t w_ready;
-  uint64_t load_z[2], a_ready[2], ds_ready[2], h_ready[2], d1_ready[2];
+  uint64_t z_full[2], z_free[2], a_ready[2], ds_ready[2], h_ready[2], d1_ready[2];
   uint32_t tmem_base;
 };
 
 template <bool BF16, bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(const __grid_constant__ CUtensorMap map_z, TcPostParams p) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* smem = tc_smem;
@@ -587,11 +618,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
   const int tiles_body = p.N * p.tiles_per_utt;
   const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
 
-  if (warp == TC_WORKER_WARPS) {
+  if (warp == TC_MMA_WARP) {
     if (lane == 0) {
       mbar_init(&bars->w_ready, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&bars->load_z[s], 256);
+        mbar_init(&bars->z_full[s], 1);
+        mbar_init(&bars->z_free[s], 256);
         mbar_init(&bars->a_ready[s], 256);
         mbar_init(&bars->ds_ready[s], 1);
         mbar_init(&bars->h_ready[s], 256);
@@ -608,9 +640,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
   const uint32_t tmem = bars->tmem_base;
   const size_t body_off = (size_t)body * p.N * p.T;
 
-  if (warp == TC_WORKER_WARPS) {
+  if (warp == TC_MMA_WARP) {
     if (elect_one()) {
-      const uint8_t* img = p.image[body];
+      const uint8_t* img = body ? p.image[1] : p.image[0];
       mbar_arrive_expect_tx(&bars->w_ready, TCP_IMAGE_BYTES);
       for (int off = 0; off < TCP_IMAGE_BYTES; off += 16384) {
         const int n = min(16384, TCP_IMAGE_BYTES - off);
@@ -651,30 +683,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
       }
     }
     __syncwarp();
+  } else if (warp == TC_TMA_WARP) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_z);
+      auto issue_z = [&](int s, int local) {
+        const int tile = cta_in_body + local * ctas_per_body;
+        const int ub = body * p.N + tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TC_TM;
+        uint8_t* st = smem + TCP_SMEM_STAGE0 + s * TCP_STAGE_BYTES;
+        mbar_arrive_expect_tx(&bars->z_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st, &map_z, 0, t0, ub, &bars->z_full[s]);
+        tma_load_3d(st + TC_BOX_BYTES, &map_z, 32, t0, ub, &bars->z_full[s]);
+      };
+      int tiles_s[2], jz[2] = {0, 0};
+      for (int s = 0; s < 2; ++s) {
+        tiles_s[s] = (n_local + 1 - s) / 2;
+        if (tiles_s[s] > 0) issue_z(s, s);
+      }
+      int s = 0;
+      while (jz[0] < tiles_s[0] || jz[1] < tiles_s[1]) {
+        if (jz[s] < tiles_s[s] && mbar_test_wait(&bars->z_free[s], jz[s] & 1)) {
+          if (jz[s] + 1 < tiles_s[s]) issue_z(s, s + 2 * (jz[s] + 1));
+          ++jz[s];
+        }
+        s ^= 1;
+      }
+    }
+    __syncwarp();
   } else {
     const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t tD = tmem + slot * 256 + lane_base;
     const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-    uint8_t* my_z = smem + TCP_SMEM_STAGE0 + slot * TCP_STAGE_BYTES + r * TC_ROW_PITCH + half * 128;
+    uint8_t* my_z = smem + TCP_SMEM_STAGE0 + slot * TCP_STAGE_BYTES + half * TC_BOX_BYTES + r * 128;
     const float* bs_s = reinterpret_cast<const float*>(smem + TCP_OFF_BS) + half * 64;
     const float* b1_s = reinterpret_cast<const float*>(smem + TCP_OFF_B1) + half * 64;
     const float* w2_s = reinterpret_cast<const float*>(smem + TCP_OFF_W2) + half * 64;
     const float* scal = reinterpret_cast<const float*>(smem + TCP_OFF_SCAL);
-    uint64_t* bar_z = &bars->load_z[slot];
-
-    auto issue_z = [&](int local) {
-      const int tile = cta_in_body + local * ctas_per_body;
-      const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
-      if (t < p.T) {
-        mbar_arrive_expect_tx(bar_z, 128);
-        bulk_g2s(my_z, p.z + (body_off + (size_t)n * p.T + t) * TC_C + half * 32, 128, bar_z);
-      } else {
-        mbar_arrive(bar_z);
-      }
-    };
-    if (slot < n_local) issue_z(slot);
     bool weights_seen = false;
     float ss = 0.f, s1 = 0.f, b2 = 0.f;
 
@@ -686,28 +731,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
       const uint32_t par = j & 1;
 
       // ---- A = z (my 32 channels: k = 32*half ..) -> fp16 hi/lo -> TMEM columns 16*half ..
-      mbar_wait(bar_z, par);
-      {
-        const float4* s4 = reinterpret_cast<const float4*>(my_z);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float v[8];
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (row_ok) { a = s4[c * 4 + q * 2]; b = s4[c * 4 + q * 2 + 1]; }
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            split8<BF16, SPLIT>(v, hi + q * 4, lo + q * 4);
-          }
-          tmem_st8(tAhi + half * 16 + c * 8, hi);
-          if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
-        }
-      }
-      if (local + 2 < n_local) {
-        fence_proxy_async_smem();
-        issue_z(local + 2);
-      }
+      mbar_wait(&bars->z_full[slot], par);
+      tc_prep<BF16, SPLIT>(my_z, r, tAhi + half * 16, tAlo + half * 16);
+      mbar_arrive(&bars->z_free[slot]);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(&bars->a_ready[slot]);
@@ -718,7 +744,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
         weights_seen = true;
       }
 
-      // ---- h = relu(skip) on my 64 of the 128 columns -> A' (k = 64*half .., columns 32*half ..)
+      // ---- h = relu(skip) on my 64 of the 128 columns -> A' (k = 64*half .., columns 32*half ..);
+      //      A' lives in the slot's A columns, disjoint from D
       mbar_wait(&bars->ds_ready[slot], par);
       tc_fence_after_sync();
 #pragma unroll
@@ -735,8 +762,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
         uint32_t hi[8], lo[8];
         split8<BF16, SPLIT>(v0, hi, lo);
         split8<BF16, SPLIT>(v1, hi + 4, lo + 4);
-        // all 256 threads of the slot have to finish READING D before anyone overwrites A? No: A'
-        // occupies the A columns (128..255 of the slot), D the first 128 -- disjoint.
         tmem_st8(tAhi + half * 32 + c * 8, hi);
         if (SPLIT) tmem_st8(tAlo + half * 32 + c * 8, lo);
       }
@@ -763,7 +788,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(TcPostParams p) {
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem, 512);
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pwv

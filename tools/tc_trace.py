@@ -15,7 +15,7 @@ weights = W.init_weights(hp, seed=0)
 m = V.PwvModel(W.model_dims(hp), weights, prec)
 noise, mel = O.synthetic_inputs(8, 16000, 80, 80)
 noise, mel = torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()
-buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device='cuda')
+buf = torch.zeros(4 * 16 * 16, dtype=torch.int64, device='cuda')
 for it in range(3):
     m.forward(noise, mel)
 torch.cuda.synchronize()
@@ -28,10 +28,10 @@ for it in range(2):
 L.check(m.lib.pwv_debug_set_trace(m._h, ctypes.c_void_p(buf.data_ptr())))
 m.forward(noise, mel)
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(3, 16, 16)
+t = buf.cpu().numpy().reshape(4, 16, 16)
 print('NOTE: the buffer holds the union of the mode-0 layer (events 0-9) and the mode-1 layer (overwrites 0-5, 8-9)')
 base = t[t > 0].min()
-names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_written', 'store_read']
+names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_ready']
 for role in (0, 1):
     print(f'--- worker slot {role} (cycles since first stamp; delta from previous event)')
     for j in range(8):
@@ -49,3 +49,8 @@ for j in range(8):
     row = t[2, j]
     if not row.any(): break
     print(f' j={j}: ' + ' '.join(f's{s}p{ph}:{row[s*8+ph*2]-base}/{row[s*8+ph*2+1]-base}' for s in (0, 1) for ph in (0, 1) if row[s*8+ph*2]))
+print('--- producer: [slot] x_refilled / out_stored / y_refilled')
+for j in range(8):
+    row = t[3, j]
+    if not row.any(): break
+    print(f' j={j}: ' + ' '.join(f's{s}:{row[s*8]-base}/{row[s*8+1]-base}/{row[s*8+2]-base}' for s in (0, 1)))
