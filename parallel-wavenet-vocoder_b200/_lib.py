@@ -79,7 +79,7 @@ def load():
     lib.pwv_forward_host.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     lib.pwv_last_launch_count.argtypes = [c.c_void_p]
     lib.pwv_set_profiling.argtypes = [c.c_void_p, c.c_int]
-    lib.pwv_debug_set_trace.argtypes = [c.c_void_p, c.c_void_p]
+    lib.pwv_debug_set_trace.argtypes = [c.c_void_p, c.c_void_p, c.c_int]
     lib.pwv_profile_read.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_int), c.POINTER(c.c_double)]
     for name in EXPORTS:
         if name not in ('pwv_last_error',):

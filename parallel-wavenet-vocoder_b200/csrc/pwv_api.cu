@@ -95,6 +95,7 @@ struct pwv_model {
 
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
+  int trace_launch = -1;         // index (among the forward's kernel launches) of the layer launch to trace
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
   int ev_used = 0;
@@ -563,7 +564,8 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : 0;
     p.tiles_per_utt = tiles_per_utt;
-    p.trace = m->trace;
+    p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+    p.trace = (m->trace && m->trace_launch == *launches) ? m->trace : nullptr;
     PWV_PROF_MARK(m, st);
     kern<<<grid, pwv::TC_THREADS, pwv::TC_SMEM_BYTES, st>>>(maps[cur], maps[cur ^ 1], p);
     PWV_PROF_MARK(m, st);
@@ -715,9 +717,10 @@ int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* 
 
 int pwv_last_launch_count(const pwv_model* m) { return m ? m->last_launches : fail(PWV_EINVAL, "null model"); }
 
-int pwv_debug_set_trace(pwv_model* m, long long* device_buffer) {
+int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int launch_index) {
   if (!m) return fail(PWV_EINVAL, "null model");
   m->trace = device_buffer;
+  m->trace_launch = launch_index;
   return PWV_OK;
 }
 

@@ -73,7 +73,11 @@ constexpr float TC_KG = -1.4426950408889634f;  // -log2(e):   b = 2^(KG*g) = e^(
 constexpr int TC_BOX_BYTES = TC_TM * 128;                 // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_BOX_BYTES;          // 64 KB
 constexpr int TC_SMEM_STAGE0 = ((TC_IMAGE_BYTES + 1023) / 1024) * 1024;
-constexpr int TC_SMEM_BYTES = TC_SMEM_STAGE0 + 2 * TC_STAGE_BYTES + 256;   // + barriers / tmem slot
+constexpr int TC_CB_FRAMES = 4;                           // conditioning rows (mel frames) staged per tile slot
+constexpr int TC_CB_BYTES = TC_CB_FRAMES * 128 * 4;
+constexpr int TC_SMEM_CB0 = TC_SMEM_STAGE0 + 2 * TC_STAGE_BYTES;
+constexpr int TC_SMEM_BARS = TC_SMEM_CB0 + 2 * TC_CB_BYTES;
+constexpr int TC_SMEM_BYTES = TC_SMEM_BARS + 256;         // + barriers / tmem slot
 
 struct TcLayerSrc {
   const float* wfg;   // host, [2C][2C] packed fp32 (tap rows, filter|gate cols)
@@ -201,6 +205,7 @@ struct TcLayerParams {
   const float* cbias[2];    // per body [N][t_mel][128], PRE-SCALED: filter half by KF, gate half by KG
   int N, T, t_mel, hop, dilation, mode;
   int tiles_per_utt;        // ceil(T / 128)
+  int cb_in_smem;           // 1: a tile spans <= TC_CB_FRAMES mel frames, its conditioning rows are staged by TMA
   long long* trace;         // debug: [4 roles][16 tiles][16 events] clock64 stamps of CTA 0 (or nullptr)
 };
 
@@ -278,13 +283,13 @@ __device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_
 
 constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
 constexpr int TC_MMA_WARP = 16;
-constexpr int TC_TMA_WARP = 17;
-constexpr int TC_THREADS = (TC_WORKER_WARPS + 2) * 32;
+constexpr int TC_TMA_WARP = 17;                           // 17, 18: TMA producer of tile slot 0, 1
+constexpr int TC_THREADS = (TC_WORKER_WARPS + 3) * 32;
 
 // barrier block at the end of dynamic shared memory
 struct TcBarriers {
   uint64_t w_ready;
-  uint64_t x_full[2], y_full[2], x_free[2], out_ready[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
+  uint64_t x_full[2], y_full[2], c_full[2], x_free[2], out_ready[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
 };
 
@@ -294,7 +299,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* smem = tc_smem;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_SMEM_STAGE0 + 2 * TC_STAGE_BYTES);
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_SMEM_BARS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int body = blockIdx.x & 1;
   const int cta_in_body = blockIdx.x >> 1, ctas_per_body = (gridDim.x + 1 - body) >> 1;
@@ -308,6 +313,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
       for (int s = 0; s < 2; ++s) {
         mbar_init(&bars->x_full[s], 1);
         mbar_init(&bars->y_full[s], 1);
+        mbar_init(&bars->c_full[s], 1);
         mbar_init(&bars->x_free[s], 256);
         mbar_init(&bars->out_ready[s], 256);
         mbar_init(&bars->a_ready[s], 256);
@@ -393,62 +399,70 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
       }
     }
     __syncwarp();
-  } else if (warp == TC_TMA_WARP) {
-    // ======================= TMA producer: activation boxes in, output boxes out =======================
+  } else if (warp >= TC_TMA_WARP) {
+    // ======================= TMA producers (one per tile slot): boxes in, output boxes out =======================
     if (elect_one()) {
+      const int s = warp - TC_TMA_WARP;
       tma_prefetch_desc(&map_in);
       tma_prefetch_desc(&map_out);
-      auto coords = [&](int local, int& ub, int& t0) {
-        const int tile = cta_in_body + local * ctas_per_body;
-        ub = body * p.N + tile / p.tiles_per_utt;          // utterance-body index (outermost map dim)
+      uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+      const float* cbias = body ? p.cbias[1] : p.cbias[0];
+      auto coords = [&](int j, int& n, int& t0) {
+        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+        n = tile / p.tiles_per_utt;
         t0 = (tile % p.tiles_per_utt) * TC_TM;
       };
-      auto issue_x = [&](int s, int local) {
-        int ub, t0;
-        coords(local, ub, t0);
-        uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+      auto issue_x = [&](int j) {
+        int n, t0;
+        coords(j, n, t0);
         mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
-        tma_load_3d(st, &map_in, 0, t0 - p.dilation, ub, &bars->x_full[s]);
-        tma_load_3d(st + TC_BOX_BYTES, &map_in, 32, t0 - p.dilation, ub, &bars->x_full[s]);
+        tma_load_3d(st, &map_in, 0, t0 - p.dilation, body * p.N + n, &bars->x_full[s]);
+        tma_load_3d(st + TC_BOX_BYTES, &map_in, 32, t0 - p.dilation, body * p.N + n, &bars->x_full[s]);
       };
-      auto issue_y = [&](int s, int local) {
-        int ub, t0;
-        coords(local, ub, t0);
-        uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES + 2 * TC_BOX_BYTES;
+      auto issue_c = [&](int j) {     // conditioning rows of the frames the tile touches (contiguous)
+        if (!p.cb_in_smem) return;
+        int n, t0;
+        coords(j, n, t0);
+        const int f0 = (t0 + p.hop / 2) / p.hop, f1 = (min(t0 + TC_TM - 1, p.T - 1) + p.hop / 2) / p.hop;
+        const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * 512;
+        mbar_arrive_expect_tx(&bars->c_full[s], bytes);
+        bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
+      };
+      const int tiles_s = (n_local + 1 - s) / 2;
+      if (tiles_s > 0) {
+        int n, t0;
+        coords(0, n, t0);
+        issue_x(0);
         mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
-        tma_load_3d(st, &map_in, 0, t0, ub, &bars->y_full[s]);
-        tma_load_3d(st + TC_BOX_BYTES, &map_in, 32, t0, ub, &bars->y_full[s]);
-      };
-      int tiles_s[2], jx[2] = {0, 0}, jo[2] = {0, 0};
-      for (int s = 0; s < 2; ++s) {
-        tiles_s[s] = (n_local + 1 - s) / 2;
-        if (tiles_s[s] > 0) { issue_x(s, s); issue_y(s, s); }
+        tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
+        tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
+        issue_c(0);
       }
-      int s = 0;
-      while (jx[0] < tiles_s[0] || jo[0] < tiles_s[0] || jx[1] < tiles_s[1] || jo[1] < tiles_s[1]) {
-        if (jx[s] < tiles_s[s] && mbar_test_wait(&bars->x_free[s], jx[s] & 1)) {
-          // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile
-          if (jx[s] + 1 < tiles_s[s]) issue_x(s, s + 2 * (jx[s] + 1));
-          TC_TRACE(3, jx[s], s * 8 + 0);
-          ++jx[s];
+      for (int j = 0; j < tiles_s; ++j) {
+        const bool more = j + 1 < tiles_s;
+        // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile
+        mbar_wait(&bars->x_free[s], j & 1);
+        if (more) issue_x(j + 1);
+        TC_TRACE(3, j, s * 8 + 0);
+        // the slot's x[t] boxes now hold the tile's output: store each, refill it as soon as it has been read
+        mbar_wait(&bars->out_ready[s], j & 1);
+        int n, t0;
+        coords(j, n, t0);
+        tma_store_3d(&map_out, 0, t0, body * p.N + n, st + 2 * TC_BOX_BYTES);
+        bulk_commit();
+        tma_store_3d(&map_out, 32, t0, body * p.N + n, st + 3 * TC_BOX_BYTES);
+        bulk_commit();
+        TC_TRACE(3, j, s * 8 + 1);
+        if (more) {
+          coords(j + 1, n, t0);
+          mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+          bulk_wait_read1();
+          tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
+          bulk_wait_read0();
+          tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
+          issue_c(j + 1);
         }
-        if (jo[s] < tiles_s[s] && mbar_test_wait(&bars->out_ready[s], jo[s] & 1)) {
-          // the slot's x[t] boxes now hold the tile's output: store, then refill for the next tile
-          int ub, t0;
-          coords(s + 2 * jo[s], ub, t0);
-          uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES + 2 * TC_BOX_BYTES;
-          tma_store_3d(&map_out, 0, t0, ub, st);
-          tma_store_3d(&map_out, 32, t0, ub, st + TC_BOX_BYTES);
-          bulk_commit();
-          TC_TRACE(3, jo[s], s * 8 + 1);
-          if (jo[s] + 1 < tiles_s[s]) {
-            bulk_wait_read0();
-            issue_y(s, s + 2 * (jo[s] + 1));
-          }
-          TC_TRACE(3, jo[s], s * 8 + 2);
-          ++jo[s];
-        }
-        s ^= 1;
+        TC_TRACE(3, j, s * 8 + 2);
       }
       bulk_wait0();
     }
@@ -497,11 +511,18 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         weights_seen = true;
       }
       const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
-      const float4* cb = reinterpret_cast<const float4*>((body ? p.cbias[1] : p.cbias[0]) + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
+      const float4* cb;
+      if (p.cb_in_smem) {               // staged by the producer: row (frame - first frame of the tile)
+        const int f0 = ((tile % p.tiles_per_utt) * TC_TM + p.hop / 2) / p.hop;
+        cb = reinterpret_cast<const float4*>(smem + TC_SMEM_CB0 + slot * TC_CB_BYTES) + (frame - f0) * 32 + half * 8;
+      } else {
+        cb = reinterpret_cast<const float4*>((body ? p.cbias[1] : p.cbias[0]) + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
+      }
 
       // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
       mbar_wait(&bars->d1_ready[slot], par);
       tc_fence_after_sync();
+      if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
       if (tracer) TC_TRACE(slot, j, 5);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -511,7 +532,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         float cf[16], cg[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 a = __ldg(cb + c * 4 + q), b = __ldg(cb + 16 + c * 4 + q);
+          const float4 a = cb[c * 4 + q], b = cb[16 + c * 4 + q];
           cf[4 * q] = a.x; cf[4 * q + 1] = a.y; cf[4 * q + 2] = a.z; cf[4 * q + 3] = a.w;
           cg[4 * q] = b.x; cg[4 * q + 1] = b.y; cg[4 * q + 2] = b.z; cg[4 * q + 3] = b.w;
         }
@@ -683,29 +704,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == TC_TMA_WARP) {
+  } else if (warp >= TC_TMA_WARP) {
     if (elect_one()) {
+      const int s = warp - TC_TMA_WARP;
       tma_prefetch_desc(&map_z);
-      auto issue_z = [&](int s, int local) {
-        const int tile = cta_in_body + local * ctas_per_body;
+      auto issue_z = [&](int j) {
+        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
         const int ub = body * p.N + tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TC_TM;
         uint8_t* st = smem + TCP_SMEM_STAGE0 + s * TCP_STAGE_BYTES;
         mbar_arrive_expect_tx(&bars->z_full[s], 2 * TC_BOX_BYTES);
         tma_load_3d(st, &map_z, 0, t0, ub, &bars->z_full[s]);
         tma_load_3d(st + TC_BOX_BYTES, &map_z, 32, t0, ub, &bars->z_full[s]);
       };
-      int tiles_s[2], jz[2] = {0, 0};
-      for (int s = 0; s < 2; ++s) {
-        tiles_s[s] = (n_local + 1 - s) / 2;
-        if (tiles_s[s] > 0) issue_z(s, s);
-      }
-      int s = 0;
-      while (jz[0] < tiles_s[0] || jz[1] < tiles_s[1]) {
-        if (jz[s] < tiles_s[s] && mbar_test_wait(&bars->z_free[s], jz[s] & 1)) {
-          if (jz[s] + 1 < tiles_s[s]) issue_z(s, s + 2 * (jz[s] + 1));
-          ++jz[s];
-        }
-        s ^= 1;
+      const int tiles_s = (n_local + 1 - s) / 2;
+      if (tiles_s > 0) issue_z(0);
+      for (int j = 0; j + 1 < tiles_s; ++j) {
+        mbar_wait(&bars->z_free[s], j & 1);
+        issue_z(j + 1);
       }
     }
     __syncwarp();

@@ -61,11 +61,16 @@ class PwvModel:
         self._ws = None
 
     def close(self):
-        if getattr(self, '_h', None) and self._h.value:
-            self.lib.pwv_model_destroy(self._h)
-            self._h = ctypes.c_void_p()
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            self.lib.pwv_model_destroy(h)
+            h.value = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: ctypes may already be torn down
+            pass
 
     def workspace_bytes(self, n, t):
         out = ctypes.c_size_t()
