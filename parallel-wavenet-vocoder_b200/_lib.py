@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpwv_b200.so')
+LIB_PATH = os.environ.get('PWV_LIB') or os.path.join(_HERE, 'libpwv_b200.so')   # PWV_LIB: A/B builds
 
 PWV_MAX_FLOWS = 8
 PWV_MAX_LAYERS = 64

@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -95,6 +96,7 @@ struct pwv_model {
 
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
+  bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
   int trace_launch = -1;         // index (among the forward's kernel launches) of the layer launch to trace
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
@@ -216,6 +218,7 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->Cc = hp->condition_channels;
   m->total_layers = total;
   m->max_layers = mx;
+  m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
   build_var_list(m);
   *out = m;
   return PWV_OK;
@@ -567,7 +570,21 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
     p.trace = (m->trace && m->trace_launch == *launches) ? m->trace : nullptr;
     PWV_PROF_MARK(m, st);
-    kern<<<grid, pwv::TC_THREADS, pwv::TC_SMEM_BYTES, st>>>(maps[cur], maps[cur ^ 1], p);
+    {
+      // programmatic dependent launch: this layer's prologue overlaps the previous kernel's tail
+      // (not while profiling: the events between the launches would serialise them anyway)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(pwv::TC_THREADS);
+      cfg.dynamicSmemBytes = pwv::TC_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = (m->profiling || !m->use_pdl) ? 0 : 1;
+      PWV_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[cur], maps[cur ^ 1], p));
+    }
     PWV_PROF_MARK(m, st);
     ++*launches;
     cur ^= 1;

@@ -197,6 +197,11 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start its prologue as SMs free
+// up / wait until the previous kernel in the stream has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

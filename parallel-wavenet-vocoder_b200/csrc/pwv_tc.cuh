@@ -26,15 +26,18 @@
 // last tiles need no masks. (Round-1 measurement that forced this: per-row 128/256-byte bulk copies
 // cost ~12 cycles of TMA issue each -- 9k cycles per tile, profiles/r1_tc_trace_v3_bulk_rows.txt.)
 //
-// Warp roles (576 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
+// Warp roles (640 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
 // A tile slot owns 256 TMEM columns (D1 128 | A1hi 64 | A1lo 64; D2 and z alias D1 / A1) and a
 // staging slot; the two slots hold alternate tiles, so one tile's epilogue overlaps the other
 // tile's MMAs. Within a slot a thread owns one row and 32 of its 64 channels (the two warps that
 // share a lane quarter split the columns), which doubles the warps available to hide the MUFU /
 // TMEM / mbarrier latencies of the epilogues. Warp 16 allocates TMEM, loads the weights and issues
-// every MMA (one elected thread), dispatching whichever slot is ready. Warp 17 is the TMA
-// producer: it refills a slot's x[t-d] boxes as soon as the workers have converted them, stores a
-// slot's output boxes when the workers have written them, then refills the x[t] boxes.
+// the slot's MMAs (one elected thread each: warps 16, 17, blocking on their slot's mbarriers). Warps
+// 18, 19 are the slots' TMA producers: each refills its slot's x[t-d] boxes as soon as the workers
+// have converted them, stores the slot's output boxes when the workers have written them, then
+// refills the x[t] boxes. The kernel is launched with programmatic stream serialization: its
+// prologue (barriers, TMEM, weight image) overlaps the previous layer's tail, and only the
+// producers' first activation load waits for the previous layer (griddepcontrol.wait).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -253,6 +256,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -282,16 +290,37 @@ __device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_
 }
 
 constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
-constexpr int TC_MMA_WARP = 16;
-constexpr int TC_TMA_WARP = 17;                           // 17, 18: TMA producer of tile slot 0, 1
-constexpr int TC_THREADS = (TC_WORKER_WARPS + 3) * 32;
+constexpr int TC_MMA_WARP = 16;                           // 16, 17: MMA issuer of tile slot 0, 1
+constexpr int TC_TMA_WARP = 18;                           // 18, 19: TMA producer of tile slot 0, 1
+constexpr int TC_THREADS = (TC_WORKER_WARPS + 4) * 32;
 
 // barrier block at the end of dynamic shared memory
 struct TcBarriers {
   uint64_t w_ready;
   uint64_t x_full[2], y_full[2], c_full[2], x_free[2], out_ready[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
+  int mma_lock;             // the two MMA issuers take turns per GEMM (keeps the slots' phases staggered)
 };
+
+// The tensor pipe executes MMAs in issue order. If both slots' issuers interleave their GEMMs, both
+// accumulators complete late and together, the two tiles' epilogues then collide on the MUFU/issue
+// ports while the tensor pipe idles (measured: +8 % kernel time). A GEMM-granular lock restores the
+// ping-pong: one slot's GEMM runs while the other slot is in its epilogue.
+// (Only worth it when a GEMM is long: the single-pass bf16 mode runs without it.)
+template <bool ENABLE>
+__device__ __forceinline__ void tc_lock(int* lock) {
+  if (ENABLE) {
+    while (atomicCAS(lock, 0, 1) != 0) {
+    }
+  }
+}
+template <bool ENABLE>
+__device__ __forceinline__ void tc_unlock(int* lock) {
+  if (ENABLE) {
+    __threadfence_block();
+    atomicExch(lock, 0);
+  }
+}
 
 template <bool BF16, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -307,6 +336,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
   // this CTA's tiles: cta_in_body, +ctas_per_body, ...; local index; tile slot s takes local % 2 == s
   const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
 
+  pdl_launch_dependents();       // the next layer's CTAs may take over SMs as ours exit
   if (warp == TC_MMA_WARP) {
     if (lane == 0) {
       mbar_init(&bars->w_ready, 1);
@@ -321,6 +351,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         mbar_init(&bars->z_ready[s], 256);
         mbar_init(&bars->d2_ready[s], 1);
       }
+      bars->mma_lock = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -331,71 +362,68 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == TC_MMA_WARP) {
-    // ======================= weights + MMA issue =======================
+  if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
+    // ======================= MMA issuers (one per tile slot); the first also loads the weights =======================
     if (elect_one()) {
-      const uint8_t* img = body ? p.image[1] : p.image[0];
-      mbar_arrive_expect_tx(&bars->w_ready, TC_IMAGE_BYTES);
-      for (int off = 0; off < TC_IMAGE_BYTES; off += 16384) {
-        const int n = min(16384, TC_IMAGE_BYTES - off);
-        bulk_g2s(smem + off, img + off, n, &bars->w_ready);
+      const int s = warp - TC_MMA_WARP;
+      if (s == 0) {
+        const uint8_t* img = body ? p.image[1] : p.image[0];
+        mbar_arrive_expect_tx(&bars->w_ready, TC_IMAGE_BYTES);
+        for (int off = 0; off < TC_IMAGE_BYTES; off += 16384) {
+          const int n = min(16384, TC_IMAGE_BYTES - off);
+          bulk_g2s(smem + off, img + off, n, &bars->w_ready);
+        }
       }
       mbar_wait(&bars->w_ready, 0);
       const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
       const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
       constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
-      // per slot: next op = 2*j + phase (phase 0: GEMM1, 1: GEMM2); mode 1 has GEMM1 only
-      int next_op[2] = {0, 0};
-      int n_ops[2];
-      for (int s = 0; s < 2; ++s) n_ops[s] = ((n_local + 1 - s) / 2) * (p.mode == 1 ? 1 : 2);
-      int s = 0;
-      while (next_op[0] < n_ops[0] || next_op[1] < n_ops[1]) {
-        if (next_op[s] < n_ops[s]) {
-          const int j = (p.mode == 1) ? next_op[s] : next_op[s] >> 1;
-          const int phase = (p.mode == 1) ? 0 : next_op[s] & 1;
-          uint64_t* ready = phase == 0 ? &bars->a_ready[s] : &bars->z_ready[s];
-          if (mbar_test_wait(ready, j & 1)) {
-            tc_fence_after_sync();
-            TC_TRACE(2, j, s * 8 + phase * 2);
-            const uint32_t tD = tmem + s * 256;
-            const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-            if (phase == 0) {
-              // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi   (K = 128: 8 steps of 16; a step = 8 TMEM columns
-              // of A and 2 K-chunks of 128 rows x 16 B of B)
-              uint32_t acc = 0;
-              if (SPLIT) {
+      const uint32_t tD = tmem + s * 256;
+      const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+      const int tiles_s = (n_local + 1 - s) / 2;
+      for (int j = 0; j < tiles_s; ++j) {
+        // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi   (K = 128: 8 steps of 16; a step = 8 TMEM columns of A
+        // and 2 K-chunks of 128 rows x 16 B of B)
+        mbar_wait(&bars->a_ready[s], j & 1);
+        tc_lock<SPLIT>(&bars->mma_lock);
+        tc_fence_after_sync();
+        TC_TRACE(2, j, s * 8 + 0);
+        uint32_t acc = 0;
+        if (SPLIT) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks, acc = 1)
-                  mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+          for (int ks = 0; ks < 8; ++ks, acc = 1)
+            mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                  mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
-              }
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks, acc = 1)
-                mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-              mma_commit(&bars->d1_ready[s]);
-            } else {
-              // D2 = z.W2 (K = 64: 4 steps; chunk = 64 rows x 16 B)
-              uint32_t acc = 0;
-              if (SPLIT) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks, acc = 1)
-                  mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
-              }
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks, acc = 1)
-                mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-              mma_commit(&bars->d2_ready[s]);
-            }
-            TC_TRACE(2, j, s * 8 + phase * 2 + 1);
-            ++next_op[s];
-          }
+          for (int ks = 0; ks < 8; ++ks)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
         }
-        s ^= 1;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks, acc = 1)
+          mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+        mma_commit(&bars->d1_ready[s]);
+        tc_unlock<SPLIT>(&bars->mma_lock);
+        TC_TRACE(2, j, s * 8 + 1);
+        if (p.mode == 1) continue;
+        // D2 = z.W2 (K = 64: 4 steps; chunk = 64 rows x 16 B)
+        mbar_wait(&bars->z_ready[s], j & 1);
+        tc_lock<SPLIT>(&bars->mma_lock);
+        tc_fence_after_sync();
+        TC_TRACE(2, j, s * 8 + 2);
+        acc = 0;
+        if (SPLIT) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks, acc = 1)
+            mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks, acc = 1)
+          mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+        mma_commit(&bars->d2_ready[s]);
+        tc_unlock<SPLIT>(&bars->mma_lock);
+        TC_TRACE(2, j, s * 8 + 3);
       }
     }
     __syncwarp();
@@ -429,6 +457,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
       };
       const int tiles_s = (n_local + 1 - s) / 2;
+      pdl_wait_prior_grid();      // the previous layer's output (and everything before it) is complete
       if (tiles_s > 0) {
         int n, t0;
         coords(0, n, t0);
@@ -538,15 +567,33 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         }
         tmem_wait_ld();
         float z[16];
+        if (BF16) {
+          // bf16 mode has no 1e-4 bar (operands carry 2^-9 relative error): one MUFU per transcendental,
+          // tanh(f) * (0.5 + 0.5 tanh(g/2)). cbias/scales hold fe = -2 log2e f, ge = -log2e g.
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          // fe = -2 log2e * f, ge = -log2e * g (cbias is pre-scaled)
-          // Only a = e^(-2f) needs an upper clamp: with a finite, b = inf gives rcp(inf) = 0 -> z = 0
-          // (the sigmoid -> 0 limit) and a, b -> 0 give z -> 1 * 1; 2^28.85: tanh = -1 + 4e-9.
-          const float fe = fminf(fmaf(__uint_as_float(fr[e]), sf, cf[e]), 28.853901f);
-          const float ge = fmaf(__uint_as_float(gr[e]), sg, cg[e]);
-          const float a = ex2_approx(fe), b = ex2_approx(ge);
-          z[e] = (1.f - a) * rcp_approx((1.f + a) * (1.f + b));
+          for (int e = 0; e < 16; ++e) {
+            const float fe = fmaf(__uint_as_float(fr[e]), sf, cf[e]);
+            const float ge = fmaf(__uint_as_float(gr[e]), sg, cg[e]);
+            const float th = tanh_approx(fe * (-0.34657359f));         // f   = fe / (-2 log2e)
+            const float tg = tanh_approx(ge * (-0.34657359f));         // g/2 = ge / (-2 log2e)
+            z[e] = th * fmaf(tg, 0.5f, 0.5f);
+          }
+        } else {
+          // a = e^(-2f) = 2^fe, b = e^(-g) = 2^ge; z = (1 - a) / ((1 + a)(1 + b)). Two channels share
+          // one reciprocal: 1/(d0 d1) * d1 = 1/d0. Clamps keep d0 d1 finite (< 2e33): tanh(10) = 1 - 4e-9,
+          // sigmoid(-18) = 1.5e-8, both far below the 1e-4 bar; a, b -> 0 on the other side is exact.
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float fe0 = fminf(fmaf(__uint_as_float(fr[e]), sf, cf[e]), 28.853901f);
+            const float ge0 = fminf(fmaf(__uint_as_float(gr[e]), sg, cg[e]), 25.968511f);
+            const float fe1 = fminf(fmaf(__uint_as_float(fr[e + 1]), sf, cf[e + 1]), 28.853901f);
+            const float ge1 = fminf(fmaf(__uint_as_float(gr[e + 1]), sg, cg[e + 1]), 25.968511f);
+            const float a0 = ex2_approx(fe0), b0 = ex2_approx(ge0), a1 = ex2_approx(fe1), b1 = ex2_approx(ge1);
+            const float d0 = (1.f + a0) * (1.f + b0), d1 = (1.f + a1) * (1.f + b1);
+            const float rinv = rcp_approx(d0 * d1);
+            z[e] = (1.f - a0) * d1 * rinv;
+            z[e + 1] = (1.f - a1) * d0 * rinv;
+          }
         }
         if (p.mode == 1) {              // last layer: z itself is the output (x[t] is dead)
 #pragma unroll
@@ -625,6 +672,7 @@ struct TcPostBarriers {
   uint64_t w_ready;
   uint64_t z_full[2], z_free[2], a_ready[2], ds_ready[2], h_ready[2], d1_ready[2];
   uint32_t tmem_base;
+  int mma_lock;
 };
 
 template <bool BF16, bool SPLIT>
@@ -650,6 +698,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(const __grid_constant
         mbar_init(&bars->h_ready[s], 256);
         mbar_init(&bars->d1_ready[s], 1);
       }
+      bars->mma_lock = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -661,46 +710,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(const __grid_constant
   const uint32_t tmem = bars->tmem_base;
   const size_t body_off = (size_t)body * p.N * p.T;
 
-  if (warp == TC_MMA_WARP) {
+  if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
     if (elect_one()) {
-      const uint8_t* img = body ? p.image[1] : p.image[0];
-      mbar_arrive_expect_tx(&bars->w_ready, TCP_IMAGE_BYTES);
-      for (int off = 0; off < TCP_IMAGE_BYTES; off += 16384) {
-        const int n = min(16384, TCP_IMAGE_BYTES - off);
-        bulk_g2s(smem + off, img + off, n, &bars->w_ready);
+      const int s = warp - TC_MMA_WARP;
+      if (s == 0) {
+        const uint8_t* img = body ? p.image[1] : p.image[0];
+        mbar_arrive_expect_tx(&bars->w_ready, TCP_IMAGE_BYTES);
+        for (int off = 0; off < TCP_IMAGE_BYTES; off += 16384) {
+          const int n = min(16384, TCP_IMAGE_BYTES - off);
+          bulk_g2s(smem + off, img + off, n, &bars->w_ready);
+        }
       }
       mbar_wait(&bars->w_ready, 0);
       const uint32_t wshi = smem_u32(smem + TCP_OFF_WSHI), wslo = smem_u32(smem + TCP_OFF_WSLO);
       const uint32_t w1hi = smem_u32(smem + TCP_OFF_W1HI), w1lo = smem_u32(smem + TCP_OFF_W1LO);
       constexpr uint32_t ID = idesc_f16(128, 128, BF16);
-      int next_op[2] = {0, 0};
-      int n_ops[2];
-      for (int s = 0; s < 2; ++s) n_ops[s] = ((n_local + 1 - s) / 2) * 2;
-      int s = 0;
-      while (next_op[0] < n_ops[0] || next_op[1] < n_ops[1]) {
-        if (next_op[s] < n_ops[s]) {
-          const int j = next_op[s] >> 1, phase = next_op[s] & 1;
-          uint64_t* ready = phase == 0 ? &bars->a_ready[s] : &bars->h_ready[s];
-          if (mbar_test_wait(ready, j & 1)) {
-            tc_fence_after_sync();
-            const uint32_t tD = tmem + s * 256;
-            const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-            const int ksteps = phase == 0 ? 4 : 8;          // K = 64 (z) / 128 (h)
-            const uint32_t bhi = phase == 0 ? wshi : w1hi, blo = phase == 0 ? wslo : w1lo;
-            uint32_t acc = 0;
-            if (SPLIT) {
-              for (int ks = 0; ks < ksteps; ++ks, acc = 1)
-                mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
-              for (int ks = 0; ks < ksteps; ++ks)
-                mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(blo + ks * 2 * 2048, 2048, 128), ID, 1);
-            }
+      const uint32_t tD = tmem + s * 256;
+      const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+      const int tiles_s = (n_local + 1 - s) / 2;
+      for (int j = 0; j < tiles_s; ++j) {
+#pragma unroll
+        for (int phase = 0; phase < 2; ++phase) {
+          mbar_wait(phase == 0 ? &bars->a_ready[s] : &bars->h_ready[s], j & 1);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          const int ksteps = phase == 0 ? 4 : 8;          // K = 64 (z) / 128 (h)
+          const uint32_t bhi = phase == 0 ? wshi : w1hi, blo = phase == 0 ? wslo : w1lo;
+          uint32_t acc = 0;
+          if (SPLIT) {
             for (int ks = 0; ks < ksteps; ++ks, acc = 1)
-              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
-            mma_commit(phase == 0 ? &bars->ds_ready[s] : &bars->d1_ready[s]);
-            ++next_op[s];
+              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
+            for (int ks = 0; ks < ksteps; ++ks)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(blo + ks * 2 * 2048, 2048, 128), ID, 1);
           }
+          for (int ks = 0; ks < ksteps; ++ks, acc = 1)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(bhi + ks * 2 * 2048, 2048, 128), ID, acc);
+          mma_commit(phase == 0 ? &bars->ds_ready[s] : &bars->d1_ready[s]);
+          tc_unlock<SPLIT>(&bars->mma_lock);
         }
-        s ^= 1;
       }
     }
     __syncwarp();
