@@ -303,22 +303,25 @@ def main():
         lm, ln, fm = model.profile_read()
         layer_ms.append(lm); layer_n = ln; fwd_ms.append(fm)
     model.set_profiling(False)
-    act_bytes = 4 if precision != 'bf16_act' else 2
-    bytes_per_launch = 2 * n * t * (2 * dims['R'] * act_bytes)           # 2 bodies x (read R + write R) per sample
-    avg_launch_s = float(np.median(layer_ms)) * 1e-3 / max(layer_n, 1)
-    achieved = bytes_per_launch / avg_launch_s / 1e9
-    mac_per_launch = 2 * n * t * (2 * dims['R'] * 2 * dims['D'] + dims['D'] * dims['R'])
+    # One launch of the gated-layer kernel runs all layers of a flow (both bodies); the algorithmic bytes
+    # are per layer: each body reads its 64-channel fp32 input once and writes its output once.
+    n_gated = sum(len(d) for d in dims['dilations'])                     # gated layers per forward (x 2 bodies each)
+    bytes_per_layer = 2 * n * t * (2 * dims['R'] * 4)
+    layer_s = float(np.median(layer_ms)) * 1e-3                          # device time of all gated-layer launches
+    achieved = n_gated * bytes_per_layer / layer_s / 1e9
+    mac_per_layer = 2 * n * t * (2 * dims['R'] * 2 * dims['D'] + dims['D'] * dims['R'])
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get(precision, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
-                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layer (both bodies)',
-                'bytes_per_launch': bytes_per_launch, 'avg_launch_us': avg_launch_s * 1e6, 'launches_per_step': layer_n,
+                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layers (tcgen05 flow kernel, both bodies)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
+                'bytes_per_launch': n_gated * bytes_per_layer / max(layer_n, 1), 'avg_launch_us': layer_s * 1e6 / max(layer_n, 1),
+                'launches_per_step': layer_n, 'gated_layers_per_step': n_gated, 'us_per_layer': layer_s * 1e6 / n_gated,
                 'share_of_step': float(np.median(layer_ms) / np.median(fwd_ms)),
-                'tflops_fp32_equiv': 2 * mac_per_launch / avg_launch_s / 1e12,
-                'note': 'compute-bound at this precision: see DESIGN.md (FLOP/B ~ 80 vs fp32 ridge ~ 10)'}
+                'tflops_fp32_equiv': 2 * n_gated * mac_per_layer / layer_s / 1e12,
+                'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); the kernel is bound by tensor/MUFU/issue, not HBM: see DESIGN.md'}
 
     # ---- e2e through the host-buffer C-ABI call
     e2e = None

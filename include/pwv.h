@@ -128,10 +128,10 @@ int pwv_last_launch_count(const pwv_model* m);
  * most recent forward and returns the summed device time of those launches, their count, and the
  * device time of the whole forward. */
 int pwv_set_profiling(pwv_model* m, int enable);
-/* Debug: device buffer of 4*16*16 int64 that CTA 0 of ONE tensor-core layer launch fills with
- * clock64() stamps of its phases (NULL switches it off). `launch_index` counts the kernel launches
- * of a forward from 0 (the first gated layer of flow 0 is launch 3). */
-int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int launch_index);
+/* Debug: device buffer of 4*16*16 int64 that CTA 0 fills with clock64() stamps of its phases while it
+ * runs ONE gated layer on the tensor cores (NULL switches it off). `layer_index` counts the gated
+ * layers of a forward from 0 with the flows concatenated (default hparams: 0..59). */
+int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int layer_index);
 int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double* forward_ms);
 
 #ifdef __cplusplus

@@ -97,7 +97,7 @@ struct pwv_model {
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
   bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
-  int trace_launch = -1;         // index (among the forward's kernel launches) of the layer launch to trace
+  int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
   int ev_used = 0;
@@ -455,6 +455,24 @@ int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes) {
 }  // extern "C"
 
 template <int C>
+static int launch_cond_gemm_c(const float* A, const pwv::RowGemmBatch& rb, int M, int K, int Z, cudaStream_t st) {
+  using Cfg = pwv::TileCfg<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_cond_gemm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((M + Cfg::TM - 1) / Cfg::TM, 1, Z);
+  pwv::k_cond_gemm<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(A, rb, M, K);
+  return PWV_OK;
+}
+static int launch_cond_gemm(int C, const float* A, const pwv::RowGemmBatch& rb, int M, int K, int Z, cudaStream_t st) {
+  if (C == 64) return launch_cond_gemm_c<64>(A, rb, M, K, Z, st);
+  if (C == 128) return launch_cond_gemm_c<128>(A, rb, M, K, Z, st);
+  return launch_cond_gemm_c<256>(A, rb, M, K, Z, st);
+}
+
+template <int C>
 static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st,
                               const pwv_taps* taps, int* cur_buf, int* launches) {
   using Cfg = pwv::TileCfg<C>;
@@ -568,7 +586,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     p.mode = (j == L - 1) ? 1 : 0;
     p.tiles_per_utt = tiles_per_utt;
     p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
-    p.trace = (m->trace && m->trace_launch == *launches) ? m->trace : nullptr;
+    p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
     PWV_PROF_MARK(m, st);
     {
       // programmatic dependent launch: this layer's prologue overlaps the previous kernel's tail
@@ -652,8 +670,13 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
                            w.cbias, (size_t)N * t_mel * 2 * C,
                            hp.precision == PWV_PREC_FP32 ? nullptr : m->d_arena + m->off_colscale};
       const int M = N * t_mel;
-      dim3 grid((2 * C + 63) / 64, (M + 63) / 64, 2 * L);
-      pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * C);
+      if (Cc % 16 == 0 && Cc <= 2 * C) {
+        rc = launch_cond_gemm(C, w.cproj, rb, M, Cc, 2 * L, st);
+        if (rc) return rc;
+      } else {
+        dim3 grid((2 * C + 63) / 64, (M + 63) / 64, 2 * L);
+        pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * C);
+      }
       ++launches;
     }
     // front: IAF combine of the previous flow + causal layers

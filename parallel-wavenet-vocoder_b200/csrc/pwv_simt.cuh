@@ -232,6 +232,62 @@ struct TileCfg {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Conditioning projections of one flow, all (body, layer) entries in one launch:
+//   out[z][m][:] = (cproj[m][:] . Wgc_z + bias_z) * colscale        m = (utterance, mel frame)
+// 64-row x 2C-column tile per CTA on the tile_gemm building block (A resident, B streamed).
+// grid = (ceil(M/64), 1, Z); K (= condition_channels) must be a multiple of 16 -- other values use
+// k_row_gemm.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(TileCfg<C>::NT) k_cond_gemm(const float* __restrict__ A, RowGemmBatch batch, int M, int K) {
+  using Cfg = TileCfg<C>;
+  constexpr int TM = Cfg::TM, NTX = Cfg::NTX, NTY = Cfg::NTY, NT = Cfg::NT;
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                       // [TM][K + 4]
+  const int lda = K + 4;
+  float* Bs = smem + TM * Cfg::LDA;       // same carve-up as the layer kernel (K <= 2C)
+  const int z = blockIdx.z, m0 = blockIdx.x * TM;
+  const int tx = threadIdx.x % NTX, ty = threadIdx.x / NTX;
+  const float* __restrict__ B = batch.B + z * batch.strideB;
+  const float* __restrict__ bias = batch.bias ? batch.bias + z * batch.strideBias : nullptr;
+  float* __restrict__ out = batch.out + z * batch.strideOut;
+  {
+    const int V = K / 4;
+    for (int e = threadIdx.x; e < TM * V; e += NT) {
+      const int m = e / V, v = e % V;
+      const bool ok = m0 + m < M;
+      cp_async16(As + (size_t)m * lda + v * 4, A + (size_t)(ok ? m0 + m : 0) * K + v * 4, ok);
+    }
+    cp_async_commit();
+  }
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  tile_gemm<NTX, NTY, 8>(As, lda, K, B, 2 * C, Bs, acc);
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;
+  if (bias) {
+    b0 = *reinterpret_cast<const float4*>(bias + 4 * tx);
+    b1 = *reinterpret_cast<const float4*>(bias + C + 4 * tx);
+  }
+  if (batch.colscale) {
+    s0 = *reinterpret_cast<const float4*>(batch.colscale + 4 * tx);
+    s1 = *reinterpret_cast<const float4*>(batch.colscale + C + 4 * tx);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty + NTY * i;
+    if (m >= M) continue;
+    float4 u, v;
+    u.x = (acc[i][0] + b0.x) * s0.x; u.y = (acc[i][1] + b0.y) * s0.y; u.z = (acc[i][2] + b0.z) * s0.z; u.w = (acc[i][3] + b0.w) * s0.w;
+    v.x = (acc[i][4] + b1.x) * s1.x; v.y = (acc[i][5] + b1.y) * s1.y; v.z = (acc[i][6] + b1.z) * s1.z; v.w = (acc[i][7] + b1.w) * s1.w;
+    *reinterpret_cast<float4*>(out + (size_t)m * 2 * C + 4 * tx) = u;
+    *reinterpret_cast<float4*>(out + (size_t)m * 2 * C + C + 4 * tx) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One gated dilated layer (reference modules.py:185-259, k=2):
 //   [f|g] = [x[t-d] | x[t]] . Wfg + cbias[frame(t)]
 //   z     = tanh(f) * sigmoid(g)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Print the phase timeline (clock64 deltas) of CTA 0 of one tensor-core gated-layer launch.
-usage: tc_trace.py [precision] [launch_index]   (default f16x3, launch 5 = layer 2 of flow 0, d=4)"""
+usage: tc_trace.py [precision] [layer_index]   (default f16x3, layer 2 of flow 0, d=4)"""
 import ctypes, importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,7 @@ hp = importlib.import_module(P + '.hparam').hparam
 W = importlib.import_module(P + '.weights'); V = importlib.import_module(P + '.vocoder'); L = importlib.import_module(P + '._lib')
 from oracle import iaf_oracle as O
 prec = sys.argv[1] if len(sys.argv) > 1 else 'f16x3'
-launch = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+launch = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 hp.set_hparam_yaml('bench/c2')
 weights = W.init_weights(hp, seed=0)
 m = V.PwvModel(W.model_dims(hp), weights, prec)
@@ -26,7 +26,7 @@ L.check(m.lib.pwv_debug_set_trace(m._h, None, -1))
 t = buf.cpu().numpy().reshape(4, 16, 16)
 base = t[t > 0].min()
 names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_ready']
-print(f'precision {prec}, launch {launch}; cycles since the first stamp (delta from the previous event)')
+print(f'precision {prec}, gated layer {launch}; cycles since the first stamp (delta from the previous event)')
 for role in (0, 1):
     print(f'--- worker slot {role}')
     for j in range(8):
