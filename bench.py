@@ -323,29 +323,61 @@ def main():
                 'tflops_fp32_equiv': 2 * n_gated * mac_per_layer / layer_s / 1e12,
                 'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); the kernel is bound by tensor/MUFU/issue, not HBM: see DESIGN.md'}
 
-    # ---- e2e through the host-buffer C-ABI call
+    # ---- e2e: host buffers in, host buffer out, copies inside the timed region.
+    #      N = 1: the C-ABI call pwv_forward_host (H2D + kernels + D2H + sync inside the call).
+    #      N > 1: rank 0 owns the whole job's pinned host batch: H2D on rank 0 -> NCCL scatter of
+    #             (noise, mel) over NVLink -> forward on every rank -> NCCL gather of wav -> D2H on rank 0
+    #             (parallel-wavenet-vocoder_b200/dist.py); timed on rank 0, max over ranks.
     e2e = None
     if not args.no_e2e:
-        pin_n = torch.from_numpy(noise_h).pin_memory()
-        pin_m = torch.from_numpy(mel_h).pin_memory()
-        pin_o = torch.empty((n, t), dtype=torch.float32).pin_memory()
-        for _ in range(2):
-            model.forward_host(pin_n, pin_m, pin_o)
-        e2e_s = 0.0
         steps_e2e = max(3, min(args.steps, 10))
-        barrier()
-        for _ in range(steps_e2e):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            model.forward_host(pin_n, pin_m, pin_o)      # H2D + kernels + D2H + sync inside
-            e2e_s += time.perf_counter() - t0
+        if world == 1:
+            pin_n = torch.from_numpy(noise_h).pin_memory()
+            pin_m = torch.from_numpy(mel_h).pin_memory()
+            pin_o = torch.empty((n, t), dtype=torch.float32).pin_memory()
+            for _ in range(2):
+                model.forward_host(pin_n, pin_m, pin_o)
+            e2e_s = 0.0
+            barrier()
+            for _ in range(steps_e2e):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                model.forward_host(pin_n, pin_m, pin_o)      # H2D + kernels + D2H + sync inside
+                e2e_s += time.perf_counter() - t0
+            api = 'pwv_forward_host (pinned host buffers)'
+            h2d, d2h = int(noise_h.nbytes + mel_h.nbytes), int(n * t * 4)
+        else:
+            D = pkg('dist')
+            n_all, t_mel = n * world, 1 + t // dims['hop']
+            if rank == 0:
+                noise_all, mel_all = O.synthetic_inputs(n_all, t, dims['hop'], dims['n_mels'])
+                pin_n = torch.from_numpy(noise_all).pin_memory()
+                pin_m = torch.from_numpy(mel_all).pin_memory()
+                pin_o = torch.empty((n_all, t), dtype=torch.float32).pin_memory()
+            def one_e2e():
+                nz = pin_n.to(dev, non_blocking=True) if rank == 0 else None
+                ml = pin_m.to(dev, non_blocking=True) if rank == 0 else None
+                full = D.sharded_forward(lambda a, b: model.forward(a, b), nz, ml, n_all, t, t_mel, dims['n_mels'], dev)
+                if rank == 0:
+                    pin_o.copy_(full, non_blocking=True)
+                torch.cuda.synchronize()
+            for _ in range(2):
+                one_e2e()
+            e2e_s = 0.0
+            for _ in range(steps_e2e):
+                flush.fill_(1)
+                barrier()
+                t0 = time.perf_counter()
+                one_e2e()
+                e2e_s += time.perf_counter() - t0
+            api = 'rank-0 pinned host batch -> H2D -> NCCL scatter -> pwv_forward per rank -> NCCL gather -> D2H'
+            h2d, d2h = int(n_all * t * 4 + n_all * t_mel * dims['n_mels'] * 4), int(n_all * t * 4)
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {'value': samples_per_step * steps_e2e / float(tt.item()), 'unit': 'samples/s',
-               'h2d_bytes_per_step': int(noise_h.nbytes + mel_h.nbytes) * world, 'd2h_bytes_per_step': int(n * t * 4) * world,
-               'steps': steps_e2e, 'api': 'pwv_forward_host (pinned host buffers)'}
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': steps_e2e, 'api': api}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None

@@ -5,9 +5,9 @@
   (mel ~ U(-1,1) as reference audio.py:278-286 normalises to, logistic noise). Reading real audio
   needs the mel front end (librosa in the reference), which is upstream of this build's scope;
   it raises with a clear message.
-* `find_checkpoint` / `load_checkpoint`: weights from `hp.logdir`. This build's container is a
-  `.npz` keyed by TF variable names (weights.py); TensorFlow bundle files (`model-*.index/.data`)
-  are recognised and reported as not yet readable.
+* `find_checkpoint` / `load_checkpoint`: weights from `hp.logdir`: TensorFlow tensor-bundle
+  checkpoints (`model-*.index` + `.data-*`, parsed natively by tf_bundle.py) or a `.npz` keyed by TF
+  variable names (weights.py).
 * `write_audio_summaries`: `audio/pred`, `audio/gt` into a TensorBoard event file in `hp.logdir`
   (reference generate.py:41-45,71-73) when tensorboard is importable, plus `.npy` copies.
 """
@@ -51,29 +51,36 @@ class GenerationData:
 
 
 def find_checkpoint(logdir, ckpt=None):
-    """`<logdir>/<ckpt>` when named (reference generate.py:55), else the newest weight file."""
+    """`<logdir>/<ckpt>` when named (reference generate.py:55), else the latest checkpoint in `logdir`:
+    a TensorFlow bundle prefix (via the `checkpoint` state file, as tf.train.latest_checkpoint does)
+    or this build's `.npz` container, whichever is newer. Returns a path or None."""
+    from . import tf_bundle
     if ckpt:
         path = os.path.join(logdir, ckpt)
+        if os.path.exists(path + '.index'):
+            return path + '.index'
         for cand in (path, path + '.npz'):
             if os.path.exists(cand):
                 return cand
-        if glob.glob(path + '.index') or glob.glob(path + '.data-*'):
-            return path + '.index'
         raise FileNotFoundError(path)
     cands = sorted(glob.glob(os.path.join(logdir, '*.npz')), key=os.path.getmtime)
-    if cands:
-        return cands[-1]
-    tf_idx = sorted(glob.glob(os.path.join(logdir, '*.index')), key=os.path.getmtime)
-    return tf_idx[-1] if tf_idx else None
+    prefix = tf_bundle.latest_checkpoint(logdir) if os.path.isdir(logdir) else None
+    if prefix and (not cands or os.path.getmtime(prefix + '.index') >= os.path.getmtime(cands[-1])):
+        return prefix + '.index'
+    return cands[-1] if cands else None
 
 
 def load_checkpoint(path, use_ema=False):
+    """name -> float32 array for every variable of the current hparams' graph. `.npz` containers are
+    keyed by TF variable names; `<prefix>.index` is a TensorFlow tensor bundle (tf_bundle.py). With
+    `use_ema` the `<name>/ExponentialMovingAverage` shadows win (reference generate.py:58-63)."""
+    from . import tf_bundle
     from . import weights as W
     if path.endswith('.npz'):
         return W.load_npz(path, use_ema=use_ema)
-    raise NotImplementedError(
-        f'{path}: TensorFlow bundle checkpoints are not readable yet; convert with '
-        f'`np.savez(path, **{{name.replace("/", "|"): value}})` keyed by TF variable names')
+    if path.endswith('.index'):
+        return tf_bundle.load_variables(path[:-len('.index')], list(W.variable_shapes(hp).keys()), use_ema=use_ema)
+    raise ValueError(f'{path}: unknown checkpoint format (expected .npz or a TensorFlow bundle .index)')
 
 
 def write_audio_summaries(logdir, sr, pred, gt=None):
