@@ -239,6 +239,9 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout carries ONE JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', '') and not os.environ.get('PWV_KEEP_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     if world != args.gpus and rank == 0:
         print(f'bench.py: note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
