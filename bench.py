@@ -248,7 +248,7 @@ def main():
 
     V, W = pkg('vocoder'), pkg('weights')
     from oracle import iaf_oracle as O          # synthetic input generator only (not the thing measured)
-    precision = args.precision or hp.engine.precision
+    precision = V.resolve_precision(W.model_dims(hp), args.precision or hp.engine.precision)
     dims = W.model_dims(hp)
     n_total, t = int(hp.generate.batch_size), int(hp.generate.length)
     n = n_total // world if args.workload == 'c4' else n_total      # c4 is strong-scaled, others weak

@@ -169,6 +169,28 @@ static void build_var_list(pwv_model* m) {
   m->loaded.assign(m->vars.size(), 0);
 }
 
+// Opt the kernels this model launches into their dynamic shared-memory sizes on the model's device
+// (per device, so it is done at finalize time with that device current).
+template <int C>
+static int configure_simt_kernels() {
+  using Cfg = pwv::TileCfg<C>;
+  PWV_CUDA(cudaFuncSetAttribute(pwv::k_cond_gemm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  return PWV_OK;
+}
+static int configure_kernels(const pwv_model* m) {
+  int rc = m->C == 64 ? configure_simt_kernels<64>() : m->C == 128 ? configure_simt_kernels<128>() : configure_simt_kernels<256>();
+  if (rc) return rc;
+  if (m->hp.precision != PWV_PREC_FP32) {
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
+  }
+  return PWV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
@@ -399,6 +421,10 @@ int pwv_model_finalize(pwv_model* m) {
     const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src, posts);
     if (err) return fail(PWV_ECUDA, "tensor-core weight images: %s", err);
   }
+  {
+    const int rc = configure_kernels(m);
+    if (rc) return rc;
+  }
   m->finalized = true;
   return PWV_OK;
 }
@@ -457,11 +483,6 @@ int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes) {
 template <int C>
 static int launch_cond_gemm_c(const float* A, const pwv::RowGemmBatch& rb, int M, int K, int Z, cudaStream_t st) {
   using Cfg = pwv::TileCfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_cond_gemm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_set = true;
-  }
   dim3 grid((M + Cfg::TM - 1) / Cfg::TM, 1, Z);
   pwv::k_cond_gemm<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(A, rb, M, K);
   return PWV_OK;
@@ -478,12 +499,6 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
   using Cfg = pwv::TileCfg<C>;
   const pwv_hparams& hp = m->hp;
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_set = true;
-  }
   dim3 grid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
   int cur = *cur_buf;
   for (int j = 0; j < L; ++j) {
@@ -560,14 +575,6 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
   const bool bf16 = hp.precision == PWV_PREC_BF16;
   auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
-    attr_set = true;
-  }
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
   const int tiles_body = N * tiles_per_utt;
   int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;

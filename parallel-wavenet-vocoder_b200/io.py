@@ -1,10 +1,9 @@
 """Inputs and outputs either side of the forward pass of `generate.py`.
 
-* `GenerationData`: the generation split of the dataset (reference data_load.py:18-25: sorted glob,
-  last 10 % when more than one file). `data_path: synthetic` yields the bench inputs instead
-  (mel ~ U(-1,1) as reference audio.py:278-286 normalises to, logistic noise). Reading real audio
-  needs the mel front end (librosa in the reference), which is upstream of this build's scope;
-  it raises with a clear message.
+* `GenerationData`: the generation split of the dataset (reference data_load.py:18-25: glob, the
+  part after `train.dataset_ratio`). `data_path: synthetic` yields the bench inputs instead
+  (mel ~ U(-1,1) as reference audio.py:278-286 normalises to, logistic noise). Real wav files go
+  through melspec.py (the reference's librosa front end restated in torch/scipy).
 * `find_checkpoint` / `load_checkpoint`: weights from `hp.logdir`: TensorFlow tensor-bundle
   checkpoints (`model-*.index` + `.data-*`, parsed natively by tf_bundle.py) or a `.npz` keyed by TF
   variable names (weights.py).
@@ -44,10 +43,15 @@ class GenerationData:
             u = np.random.RandomState(int(engine.get('noise_seed', 1235))).uniform(1e-7, 1 - 1e-7, size=(n, t))
             noise = (np.log(u) - np.log1p(-u)).astype(np.float32)
             return None, mel, noise
-        raise NotImplementedError(
-            'reading wav files needs the mel front end (reference data_load.py:37-56 -> audio.py:341-356, '
-            'librosa), which is outside this build; use a case with data_path: synthetic, or call '
-            'models.IAFVocoder directly with your own mel-spectrogram')
+        from . import melspec
+        if not self.wav_files:
+            raise FileNotFoundError(f'no wav files match data_path {hp.data_path!r}')
+        wavs, mels = [], []
+        for i in range(n):                       # the reference batches consecutive (shuffled) files; here: in order
+            wav, mel = melspec.wav_and_melspec(self.wav_files[i % len(self.wav_files)], hp.signal, t)
+            wavs.append(wav)
+            mels.append(mel)
+        return np.stack(wavs), np.stack(mels), None
 
 
 def find_checkpoint(logdir, ckpt=None):

@@ -34,12 +34,21 @@ def _assert_supported(hp):
         raise AssertionError(f'prod({strides}) != hop_length {hp.signal.hop_length} (reference models.py:106)')
 
 
+def resolve_precision(dims, precision):
+    """'auto' -> 'f16x3' (tcgen05, fp32-level parity) when the tensor-core kernels cover the channel
+    count (R = D = 64, S = 128), else the exact fp32 FFMA kernels."""
+    if precision in (None, '', 'auto'):
+        return 'f16x3' if (dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128) else 'fp32'
+    return precision
+
+
 class PwvModel:
     """Thin RAII wrapper over a finalized `pwv_model`."""
 
-    def __init__(self, dims, weights, precision='fp32'):
+    def __init__(self, dims, weights, precision='auto'):
         self.lib = _lib.load()
         self.dims = dims
+        precision = resolve_precision(dims, precision)
         self.precision = precision
         self._h = ctypes.c_void_p()
         hparams = _lib.make_hparams(dims, precision)
@@ -180,7 +189,7 @@ class IAFVocoder:
         self.device = torch.device(device)
         self.dims = W.model_dims(hp)
         engine = hp.get('engine', {}) or {}
-        self.precision = engine.get('precision', 'fp32')
+        self.precision = resolve_precision(self.dims, engine.get('precision', 'auto'))
         if weights is None:      # a fresh reference graph: Glorot kernels, zero biases (generate.py:56)
             weights = W.init_weights(hp, seed=int(engine.get('seed', 0)))
         W.check_weights(hp, weights)

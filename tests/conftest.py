@@ -27,6 +27,7 @@ def hp():
 
 
 def small_case(hp, channels=64, dilations=((1, 2, 4, 512), (1, 8, 64)), n=2, t=1600, precision='fp32'):
+    """A small graph; `precision` defaults to the exact fp32 kernels (tests opt in to the tensor-core modes)."""
     hp.set_hparam_dict({
         'model': {'n_iaf': len(dilations), 'dilations': [list(d) for d in dilations],
                   'residual_channels': channels, 'dilation_channels': channels, 'skip_channels': 2 * channels},

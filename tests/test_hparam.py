@@ -27,6 +27,8 @@ def test_case_overrides_merge_recursively(hp):
     assert hp.model.cond_upsample_method == 'transposed_conv' and hp.model.n_iaf == 4
     hp.set_hparam_yaml('bench/c3')
     assert hp.signal.sr == 24000 and hp.generate.length == 96000 and hp.engine.precision == 'bf16'
+    hp.set_hparam_yaml('bench/c2')
+    assert hp.engine.precision == 'f16x3' and hp.engine.seed == 0
 
 
 def test_unknown_case_falls_back_to_defaults(hp):
