@@ -585,6 +585,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   int cur = *cur_buf;
   for (int j = 0; j < L; ++j) {
     pwv::TcLayerParams p;
+    p.x_out = w.act[cur ^ 1];
     for (int b = 0; b < 2; ++b) {
       p.image[b] = m->tc.d_images + (layer_base + (size_t)b * L + j) * pwv::TC_IMAGE_BYTES;
       p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
@@ -608,7 +609,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = (m->profiling || !m->use_pdl) ? 0 : 1;
-      PWV_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[cur], maps[cur ^ 1], p));
+      PWV_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[cur], p));
     }
     PWV_PROF_MARK(m, st);
     ++*launches;

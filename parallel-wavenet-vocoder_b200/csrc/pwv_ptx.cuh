@@ -93,6 +93,9 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, i
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) { asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory"); }
 
+// named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ----------------------------------------------------------------------------- TMEM
 // Allocate `ncols` (power of two >= 32) TMEM columns; one full warp calls this; the base address
 // is written to *slot (shared memory).

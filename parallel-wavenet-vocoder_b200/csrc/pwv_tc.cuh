@@ -20,10 +20,11 @@
 // Operand placement: A operands (activations, z) live in TMEM (written by the epilogue threads
 // with tcgen05.st, two 16-bit elements per column), B operands (weights) in shared memory in the
 // K-major no-swizzle core-matrix layout, loaded once per CTA by 1-D bulk copies (TMA unit).
-// Activations move HBM <-> shared memory as TMA tensor boxes (128 rows x 32 channels, 128B swizzle)
-// of a 3-D map [2N utterance-bodies][T][64]: rows before an utterance's start or past its end are
-// zero-filled on load and dropped on store by the TMA unit, so the causal zero history and ragged
-// last tiles need no masks. (Round-1 measurement that forced this: per-row 128/256-byte bulk copies
+// Activations come in as TMA tensor boxes (128 rows x 32 channels, 128B swizzle) of a 3-D map
+// [2N utterance-bodies][T][64]: rows before an utterance's start or past its end are zero-filled by
+// the TMA unit, so the causal zero history and ragged last tiles need no masks on the way in. The
+// output is written in place into the x[t] boxes and copied out by the same warps with full-line
+// stores, after which the boxes are refilled at once. (Round-1 measurement that forced this: per-row 128/256-byte bulk copies
 // cost ~12 cycles of TMA issue each -- 9k cycles per tile, profiles/r1_tc_trace_v3_bulk_rows.txt.)
 //
 // Warp roles (640 threads): 16 worker warps = 2 tile slots x 2 channel halves x 4 lane quarters.
@@ -34,8 +35,7 @@
 // TMEM / mbarrier latencies of the epilogues. Warp 16 allocates TMEM, loads the weights and issues
 // the slot's MMAs (one elected thread each: warps 16, 17, blocking on their slot's mbarriers). Warps
 // 18, 19 are the slots' TMA producers: each refills its slot's x[t-d] boxes as soon as the workers
-// have converted them, stores the slot's output boxes when the workers have written them, then
-// refills the x[t] boxes. The kernel is launched with programmatic stream serialization: its
+// have converted them and the x[t] boxes (and conditioning rows) once the output has been copied out. The kernel is launched with programmatic stream serialization: its
 // prologue (barriers, TMEM, weight image) overlaps the previous layer's tail, and only the
 // producers' first activation load waits for the previous layer (griddepcontrol.wait).
 #pragma once
@@ -204,6 +204,7 @@ inline const char* tc_model_build(TcModel& t, int precision, int C, const std::v
 // device side
 // ------------------------------------------------------------------------------------------------
 struct TcLayerParams {
+  float* x_out;             // [2][N][T][64]: the layer's output (mode 1: z)
   const uint8_t* image[2];  // per body
   const float* cbias[2];    // per body [N][t_mel][128], PRE-SCALED: filter half by KF, gate half by KG
   int N, T, t_mel, hop, dilation, mode;
@@ -297,7 +298,7 @@ constexpr int TC_THREADS = (TC_WORKER_WARPS + 4) * 32;
 // barrier block at the end of dynamic shared memory
 struct TcBarriers {
   uint64_t w_ready;
-  uint64_t x_full[2], y_full[2], c_full[2], x_free[2], out_ready[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
+  uint64_t x_full[2], y_full[2], c_full[2], x_free[2], y_free[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
   int mma_lock;             // the two MMA issuers take turns per GEMM (keeps the slots' phases staggered)
 };
@@ -324,7 +325,7 @@ __device__ __forceinline__ void tc_unlock(int* lock) {
 
 template <bool BF16, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, TcLayerParams p) {
+k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* smem = tc_smem;
@@ -345,7 +346,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         mbar_init(&bars->y_full[s], 1);
         mbar_init(&bars->c_full[s], 1);
         mbar_init(&bars->x_free[s], 256);
-        mbar_init(&bars->out_ready[s], 256);
+        mbar_init(&bars->y_free[s], 256);
         mbar_init(&bars->a_ready[s], 256);
         mbar_init(&bars->d1_ready[s], 1);
         mbar_init(&bars->z_ready[s], 256);
@@ -432,7 +433,6 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
     if (elect_one()) {
       const int s = warp - TC_TMA_WARP;
       tma_prefetch_desc(&map_in);
-      tma_prefetch_desc(&map_out);
       uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
       const float* cbias = body ? p.cbias[1] : p.cbias[0];
       auto coords = [&](int j, int& n, int& t0) {
@@ -458,6 +458,10 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
       };
       const int tiles_s = (n_local + 1 - s) / 2;
       pdl_wait_prior_grid();      // the previous layer's output (and everything before it) is complete
+      // Slot 1 lets slot 0's first boxes land before asking for its own: the TMA unit moves ~40 B/clk, so
+      // interleaving both slots' 64 KB would deliver both at ~4k cycles; this way slot 0 starts at ~2k and
+      // the two tiles begin half a phase apart, which is where the ping-pong wants them anyway.
+      if (s == 1 && n_local > 0) mbar_wait(&bars->y_full[0], 0);
       if (tiles_s > 0) {
         int n, t0;
         coords(0, n, t0);
@@ -467,33 +471,22 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
         tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
         issue_c(0);
       }
-      for (int j = 0; j < tiles_s; ++j) {
-        const bool more = j + 1 < tiles_s;
+      for (int j = 0; j + 1 < tiles_s; ++j) {
         // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile
         mbar_wait(&bars->x_free[s], j & 1);
-        if (more) issue_x(j + 1);
+        issue_x(j + 1);
         TC_TRACE(3, j, s * 8 + 0);
-        // the slot's x[t] boxes now hold the tile's output: store each, refill it as soon as it has been read
-        mbar_wait(&bars->out_ready[s], j & 1);
+        // the workers have copied the tile's output out of the x[t] boxes and are done with the
+        // conditioning rows: refill both for the next tile
+        mbar_wait(&bars->y_free[s], j & 1);
         int n, t0;
-        coords(j, n, t0);
-        tma_store_3d(&map_out, 0, t0, body * p.N + n, st + 2 * TC_BOX_BYTES);
-        bulk_commit();
-        tma_store_3d(&map_out, 32, t0, body * p.N + n, st + 3 * TC_BOX_BYTES);
-        bulk_commit();
-        TC_TRACE(3, j, s * 8 + 1);
-        if (more) {
-          coords(j + 1, n, t0);
-          mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
-          bulk_wait_read1();
-          tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
-          bulk_wait_read0();
-          tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
-          issue_c(j + 1);
-        }
+        coords(j + 1, n, t0);
+        mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
+        tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
+        issue_c(j + 1);
         TC_TRACE(3, j, s * 8 + 2);
       }
-      bulk_wait0();
     }
     __syncwarp();
   } else {
@@ -634,10 +627,25 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ C
           *box_chunk(my_y, r, q) = o;
         }
       }
-      // ---- hand the output boxes to the producer (generic writes -> async proxy)
+      // ---- the tile's output sits in the x[t] boxes (my half: 128 rows x 128 B, swizzled). The four warps of
+      //      this (slot, half) copy it out with full-line stores: a warp instruction writes 4 rows x 128 B.
+      //      (Per-thread row stores and a TMA store were both measured slower: the former issues 32 partial
+      //      lines per instruction, the latter holds the boxes ~1.5k cycles while the TMA unit drains them.)
+      named_bar_sync(1 + slot * 2 + half, 128);
+      {
+        uint8_t* box = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES;
+        const int t_first = (tile % p.tiles_per_utt) * TC_TM;
+        float* out_tile = p.x_out + (((size_t)body * p.N + n) * p.T + t_first) * TC_C + half * 32;
+        const int chunk = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = quarter * 32 + i * 4 + (lane >> 3);
+          const float4 v = *box_chunk(box + row * 128, row, chunk);
+          if (t_first + row < p.T) *reinterpret_cast<float4*>(out_tile + (size_t)row * TC_C + chunk * 4) = v;
+        }
+      }
       tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->out_ready[slot]);
+      mbar_arrive(&bars->y_free[slot]);          // (release: my reads of the x[t] boxes and conditioning rows are done)
       if (tracer) TC_TRACE(slot, j, 8);
     }
   }
