@@ -187,6 +187,10 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
+    if (m->tc.d_cond) {
+      PWV_CUDA(cudaFuncSetAttribute(pwv::k_cbias_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::tcc_smem_bytes(m->Cc)));
+      PWV_CUDA(cudaFuncSetAttribute(pwv::k_cbias_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::tcc_smem_bytes(m->Cc)));
+    }
   }
   return PWV_OK;
 }
@@ -420,6 +424,17 @@ int pwv_model_finalize(pwv_model* m) {
       }
     const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src, posts);
     if (err) return fail(PWV_ECUDA, "tensor-core weight images: %s", err);
+    // conditioning projections on the tensor cores too (when Cc allows it)
+    std::vector<pwv::TcCondSrc> csrc;
+    for (int i = 0; i < hp.n_iaf; ++i)
+      for (int e = 0; e < 2 * hp.n_layers[i]; ++e) {
+        pwv::TcCondSrc q;
+        q.wgc = arena.data() + m->off_wgc[i] + (size_t)e * Cc * 2 * C;
+        q.bias = arena.data() + m->off_bfg[i] + (size_t)e * 2 * C;
+        csrc.push_back(q);
+      }
+    err = pwv::tc_cond_build(m->tc, hp.precision, Cc, arena.data() + m->off_colscale, csrc);
+    if (err) return fail(PWV_ECUDA, "tensor-core conditioning images: %s", err);
   }
   {
     const int rc = configure_kernels(m);
@@ -678,7 +693,22 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
                            w.cbias, (size_t)N * t_mel * 2 * C,
                            hp.precision == PWV_PREC_FP32 ? nullptr : m->d_arena + m->off_colscale};
       const int M = N * t_mel;
-      if (Cc % 16 == 0 && Cc <= 2 * C) {
+      if (hp.precision != PWV_PREC_FP32 && m->tc.d_cond) {
+        pwv::TcCondParams q;
+        size_t zbase = 0;
+        for (int f = 0; f < i; ++f) zbase += 2 * (size_t)hp.n_layers[f];
+        q.cproj = w.cproj;
+        q.images = m->tc.d_cond + zbase * m->tc.cond_image_bytes;
+        q.out = w.cbias;
+        q.out_stride = (size_t)M * 2 * C;
+        q.M = M; q.Cc = Cc; q.Z = 2 * L; q.image_bytes = m->tc.cond_image_bytes;
+        const int m_tiles = (M + pwv::TC_TM - 1) / pwv::TC_TM;
+        int zsplit = m->num_sms / m_tiles;
+        zsplit = zsplit < 1 ? 1 : (zsplit > 2 * L ? 2 * L : zsplit);
+        dim3 grid(m_tiles, zsplit);
+        if (hp.precision == PWV_PREC_BF16) pwv::k_cbias_tc<true, false><<<grid, pwv::TCC_THREADS, pwv::tcc_smem_bytes(Cc), st>>>(q);
+        else pwv::k_cbias_tc<false, true><<<grid, pwv::TCC_THREADS, pwv::tcc_smem_bytes(Cc), st>>>(q);
+      } else if (Cc % 16 == 0 && Cc <= 2 * C) {
         rc = launch_cond_gemm(C, w.cproj, rb, M, Cc, 2 * L, st);
         if (rc) return rc;
       } else {

@@ -91,6 +91,8 @@ struct TcLayerSrc {
 struct TcModel {
   uint8_t* d_images = nullptr;   // [n_layers_total] x TC_IMAGE_BYTES, order = (flow, body, layer)
   uint8_t* d_post = nullptr;     // [n_iaf * 2] x TCP_IMAGE_BYTES, order = (flow, body)
+  uint8_t* d_cond = nullptr;     // [n_layers_total] x cond_image_bytes, order = (flow, body, layer); may stay null
+  int cond_image_bytes = 0;
   size_t bytes = 0;
   int precision = 0;
 };
@@ -156,9 +158,47 @@ inline void tc_pack_b(uint8_t* hi, uint8_t* lo, const float* w, int K, int Ncols
 inline void tc_model_free(TcModel& t) {
   if (t.d_images) cudaFree(t.d_images);
   if (t.d_post) cudaFree(t.d_post);
+  if (t.d_cond) cudaFree(t.d_cond);
   t.d_images = nullptr;
   t.d_post = nullptr;
+  t.d_cond = nullptr;
+  t.cond_image_bytes = 0;
   t.bytes = 0;
+}
+
+// Conditioning projection image of one (flow, body, layer): B[n = 128][k = Cc] = [gc_filter | gc_gate]
+// as fp16 hi / lo K-major chunks, then colmul[128] = colscale / 2^s and coladd[128] = bias * colscale
+// (out = acc * colmul + coladd = (cproj . Wgc + bias) * colscale).
+constexpr int TCC_MAX_CC = 96;            // two weight images + the cproj tile + the output tile must fit 227 KB
+inline int tcc_image_bytes(int Cc) { return ((2 * (Cc / 8) * 2048 + 1024) + 1023) / 1024 * 1024; }
+inline int tcc_a_pitch(int Cc) { return Cc * 4 + 16; }          // staged cproj row + 16 B (bank spread)
+inline int tcc_smem_bytes(int Cc) { return 2 * tcc_image_bytes(Cc) + ((128 * tcc_a_pitch(Cc) + 1023) / 1024 * 1024) + 128 * 512 + 256; }
+struct TcCondSrc {
+  const float* wgc;       // host [Cc][128]
+  const float* bias;      // host [128]
+};
+inline const char* tc_cond_build(TcModel& t, int precision, int Cc, const float* colscale, const std::vector<TcCondSrc>& src) {
+  if (Cc % 16 != 0 || Cc > TCC_MAX_CC) return nullptr;   // the FFMA conditioning kernel is used instead
+  const bool bf16 = precision == 2, split = precision == 1;
+  const int img_bytes = tcc_image_bytes(Cc), half_bytes = (Cc / 8) * 2048;
+  std::vector<uint8_t> host(src.size() * (size_t)img_bytes, 0);
+  for (size_t i = 0; i < src.size(); ++i) {
+    uint8_t* img = host.data() + i * (size_t)img_bytes;
+    const float sc = bf16 ? 1.f : tc_pow2_scale(src[i].wgc, (size_t)Cc * 128);
+    tc_pack_b(img, img + half_bytes, src[i].wgc, Cc, 128, sc, bf16, split);
+    float* vec = reinterpret_cast<float*>(img + 2 * half_bytes);
+    for (int n = 0; n < 128; ++n) {
+      vec[n] = colscale[n] / sc;
+      vec[128 + n] = src[i].bias[n] * colscale[n];
+    }
+  }
+  if (t.d_cond) cudaFree(t.d_cond);
+  t.d_cond = nullptr;
+  if (cudaMalloc(&t.d_cond, host.size()) != cudaSuccess) return "cudaMalloc of the conditioning weight images failed";
+  if (cudaMemcpy(t.d_cond, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) return "upload of the conditioning weight images failed";
+  t.cond_image_bytes = img_bytes;
+  t.bytes += host.size();
+  return nullptr;
 }
 
 // precision: 1 = f16x3, 2 = bf16. Returns nullptr on success or a static error string.
@@ -854,6 +894,190 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_post_tc(const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conditioning rows of one flow on the tensor cores: for every (body, layer) z of the flow
+//   out_z[m][0:128] = (cproj[m][0:Cc] . Wgc_z + bias_z) * colscale          m = (utterance, mel frame)
+// (reference modules.py:216-228 at mel rate; 1.3 % of the path's FLOPs, 4 % of its time on CUDA cores).
+// A CTA owns one 128-row tile of cproj -- split once into fp16 hi/lo and parked in TMEM -- and walks a
+// strided subset of the z entries, streaming their weight images through a 2-deep shared-memory ring;
+// accumulators are double-buffered in TMEM so the epilogue of entry b overlaps the MMAs of b+1. The
+// output tile (128 x 128 fp32) goes through a swizzled staging tile and leaves as full 512-byte rows.
+// grid = (ceil(M/128), zsplit); 320 threads: 8 worker warps, 1 MMA warp, 1 producer warp.
+// ------------------------------------------------------------------------------------------------
+struct TcCondParams {
+  const float* cproj;       // [M][Cc]
+  const uint8_t* images;    // entry z at images + z * image_bytes
+  float* out;               // entry z at out + z * out_stride
+  size_t out_stride;        // floats (= M * 128)
+  int M, Cc, Z, image_bytes;
+};
+
+constexpr int TCC_THREADS = 320;
+// shared memory: [2 weight images][cproj tile, rows of Cc*4+16 B][output tile 128 x 512 B, 16-byte chunks
+// XOR-swizzled by row][barriers]; sizes depend on Cc (tcc_smem_bytes)
+
+struct TcCondBarriers {
+  uint64_t a_full, a_ready, w_full[2], w_free[2], d_ready[2], d_free[2];
+  uint32_t tmem_base;
+};
+
+template <bool BF16, bool SPLIT>
+__global__ void __launch_bounds__(TCC_THREADS, 1) k_cbias_tc(TcCondParams p) {
+  using namespace ptx;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* smem = tc_smem;
+  const int a_pitch = p.Cc * 4 + 16;
+  const int TCC_W_BYTES = p.image_bytes;
+  const int TCC_SMEM_W0 = 0;
+  const int TCC_SMEM_A = 2 * TCC_W_BYTES;
+  const int TCC_SMEM_OUT = TCC_SMEM_A + (128 * a_pitch + 1023) / 1024 * 1024;
+  const int TCC_SMEM_BARS = TCC_SMEM_OUT + 128 * 512;
+  TcCondBarriers* bars = reinterpret_cast<TcCondBarriers*>(smem + TCC_SMEM_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_TM;
+  const int zsplit = gridDim.y, z0 = blockIdx.y;
+  const int nb = (p.Z > z0) ? (p.Z - z0 + zsplit - 1) / zsplit : 0;      // entries z0, z0 + zsplit, ...
+  const int ksteps = p.Cc / 16, half_bytes = (p.Cc / 8) * 2048;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(&bars->a_full, 1);
+      mbar_init(&bars->a_ready, 256);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->w_full[i], 1);
+        mbar_init(&bars->w_free[i], 1);
+        mbar_init(&bars->d_ready[i], 1);
+        mbar_init(&bars->d_free[i], 256);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;      // D0 [0,128) | D1 [128,256) | Ahi [256,320) | Alo [320,384)
+
+  if (warp == 8) {
+    // ---------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t ID = idesc_f16(128, 128, BF16);
+      mbar_wait(&bars->a_ready, 0);
+      for (int b = 0; b < nb; ++b) {
+        const int buf = b & 1;
+        const uint32_t use = (uint32_t)(b >> 1) & 1;
+        mbar_wait(&bars->w_full[buf], use);
+        mbar_wait(&bars->d_free[buf], use ^ 1);        // (first use of each buffer passes immediately)
+        tc_fence_after_sync();
+        const uint32_t whi = smem_u32(smem + TCC_SMEM_W0 + buf * TCC_W_BYTES), wlo = whi + half_bytes;
+        const uint32_t tD = tmem + buf * 128, tAhi = tmem + 256, tAlo = tmem + 320;
+        uint32_t acc = 0;
+        if (SPLIT) {
+          for (int ks = 0; ks < ksteps; ++ks, acc = 1)
+            mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(whi + ks * 2 * 2048, 2048, 128), ID, acc);
+          for (int ks = 0; ks < ksteps; ++ks)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(wlo + ks * 2 * 2048, 2048, 128), ID, 1);
+        }
+        for (int ks = 0; ks < ksteps; ++ks, acc = 1)
+          mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(whi + ks * 2 * 2048, 2048, 128), ID, acc);
+        mma_commit(&bars->d_ready[buf]);
+        mma_commit(&bars->w_free[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ---------------- producer: the cproj tile once, then the weight images
+    if (elect_one()) {
+      const int rows = min(TC_TM, p.M - m0);
+      mbar_arrive_expect_tx(&bars->a_full, (uint32_t)rows * p.Cc * 4);
+      for (int r = 0; r < rows; ++r)
+        bulk_g2s(smem + TCC_SMEM_A + r * a_pitch, p.cproj + (size_t)(m0 + r) * p.Cc, p.Cc * 4, &bars->a_full);
+      for (int b = 0; b < nb; ++b) {
+        const int buf = b & 1;
+        const uint32_t use = (uint32_t)(b >> 1) & 1;
+        if (b >= 2) {
+          mbar_wait(&bars->w_free[buf], use ^ 1);      // the MMAs of entry b-2 have read the buffer ...
+          mbar_wait(&bars->d_free[buf], use ^ 1);      // ... and the workers its colmul / coladd vectors
+        }
+        const int z = z0 + b * zsplit;
+        mbar_arrive_expect_tx(&bars->w_full[buf], (uint32_t)p.image_bytes);
+        bulk_g2s(smem + TCC_SMEM_W0 + buf * TCC_W_BYTES, p.images + (size_t)z * p.image_bytes, p.image_bytes, &bars->w_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- workers: thread = (row, 64 of the 128 output columns)
+    const int half = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool row_ok = m0 + r < p.M;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    // A: k range of this half: [0, kh) / [kh, Cc) with kh a multiple of 16 so that tcgen05.st widths fit
+    mbar_wait(&bars->a_full, 0);
+    {
+      const float4* arow = reinterpret_cast<const float4*>(smem + TCC_SMEM_A + r * a_pitch);
+      const int k_per_half = p.Cc / 2;               // Cc % 16 == 0 -> multiple of 8
+      const int kb = half * k_per_half;
+      for (int k = kb; k < kb + k_per_half; k += 8) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a;
+        if (row_ok) { a = arow[k / 4]; b4 = arow[k / 4 + 1]; }
+        const float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        uint32_t hi[4], lo[4];
+        split8<BF16, SPLIT>(v, hi, lo);
+        tmem_st4(tmem + 256 + lane_base + k / 2, hi);
+        if (SPLIT) tmem_st4(tmem + 320 + lane_base + k / 2, lo);
+      }
+    }
+    tmem_wait_st();
+    tc_fence_before_sync();
+    mbar_arrive(&bars->a_ready);
+
+    uint8_t* stage_row = smem + TCC_SMEM_OUT + r * 512;
+    for (int b = 0; b < nb; ++b) {
+      const int buf = b & 1;
+      const uint32_t use = (uint32_t)(b >> 1) & 1;
+      const int z = z0 + b * zsplit;
+      const float* vec = reinterpret_cast<const float*>(smem + TCC_SMEM_W0 + buf * TCC_W_BYTES + 2 * half_bytes);
+      mbar_wait(&bars->d_ready[buf], use);
+      tc_fence_after_sync();
+      const uint32_t tD = tmem + buf * 128 + lane_base + half * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t dr[16];
+        tmem_ld16(tD + c * 16, dr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = half * 64 + c * 16 + q * 4;
+          const float4 mul = *reinterpret_cast<const float4*>(vec + col);
+          const float4 add = *reinterpret_cast<const float4*>(vec + 128 + col);
+          float4 o;
+          o.x = fmaf(__uint_as_float(dr[4 * q + 0]), mul.x, add.x);
+          o.y = fmaf(__uint_as_float(dr[4 * q + 1]), mul.y, add.y);
+          o.z = fmaf(__uint_as_float(dr[4 * q + 2]), mul.z, add.z);
+          o.w = fmaf(__uint_as_float(dr[4 * q + 3]), mul.w, add.w);
+          const int chunk = col >> 2;                       // 16-byte chunk 0..31 of the row
+          *reinterpret_cast<float4*>(stage_row + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4)) = o;
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bars->d_free[buf]);                      // accumulator and weight vectors of entry b consumed
+      named_bar_sync(1, 256);                               // the whole tile is staged
+      float* out_tile = p.out + (size_t)z * p.out_stride + (size_t)m0 * 128;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {                        // a warp instruction writes one full 512-byte row
+        const int row = warp * 16 + i;
+        const float4 v = *reinterpret_cast<const float4*>(smem + TCC_SMEM_OUT + row * 512 + (((lane & ~7) | ((lane ^ row) & 7)) << 4));
+        if (m0 + row < p.M) *reinterpret_cast<float4*>(out_tile + (size_t)row * 128 + lane * 4) = v;
+      }
+      named_bar_sync(1, 256);                               // staging tile free for the next entry
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pwv

@@ -174,3 +174,17 @@ def test_bf16_mode_runs_and_reports_drift(hp):
     err = np.abs(out.cpu().numpy() - ref).max()
     print('bf16 default hparams max|delta| =', err)
     assert np.isfinite(err) and err < 0.2
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
+@pytest.mark.parametrize('n_mels,cc', [(40, 48), (80, 20)])
+def test_other_conditioning_widths(hp, n_mels, cc, precision):
+    """condition_channels a multiple of 16 (tile_gemm conditioning kernel, K=48) and not (row-GEMM fallback, K=20)."""
+    hp.set_hparam_dict({'model': {'n_iaf': 2, 'dilations': [[1, 2, 4], [8, 1]], 'condition_channels': cc},
+                        'signal': {'n_mels': n_mels}, 'generate': {'batch_size': 2, 'length': 800},
+                        'engine': {'precision': precision}}, case='test/cond')
+    weights = pkg('weights').init_weights(hp, seed=9, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(2, 800, 80, n_mels)
+    ref = _oracle(hp, weights, noise, mel)
+    out, _ = _run(hp, weights, noise, mel)
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL
