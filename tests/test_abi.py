@@ -126,3 +126,17 @@ def test_product_path_never_imports_the_oracle():
             if os.path.exists(p) and re.search(r'^\s*(from|import)\s+oracle\b|oracle[./]iaf_oracle', open(p).read(), flags=re.M):
                 offenders.append(p)
     assert not offenders, offenders
+
+
+def test_plain_c_consumer_builds_and_runs(tmp_path):
+    """include/pwv.h compiles as C (gcc -std=c99 -pedantic) and a C program drives the library."""
+    import subprocess
+    L = pkg('_lib')
+    L.load()
+    exe = str(tmp_path / 'c_abi_smoke')
+    src = os.path.join(ROOT, 'tests', 'c_abi_smoke.c')
+    subprocess.run(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-o', exe, src, L.LIB_PATH,
+                    '-Wl,-rpath,' + os.path.dirname(L.LIB_PATH)], check=True)
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0, out.stdout
+    assert 'c_abi_smoke ok' in out.stdout
