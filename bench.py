@@ -201,13 +201,30 @@ def run_reference_arm(args, hp, rank, world):
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class StdoutGuard:
+    """stdout carries exactly ONE JSON line: anything native libraries write to fd 1 meanwhile (NCCL's
+    version banner, for one) is diverted to stderr until the line is printed."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -228,7 +245,9 @@ def main():
     hp.set_hparam_yaml(WORKLOADS[args.workload][0])
 
     if args.impl == 'reference':
-        run_reference_arm(args, hp, rank, world)
+        line = run_reference_arm(args, hp, rank, world)
+        if line is not None:
+            guard.emit(json.dumps(line))
         return
 
     import torch
@@ -401,7 +420,7 @@ def main():
                        'l2': 'flushed (256 MB write) before every timed step', 'timing': 'CUDA events per step, max over ranks'},
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

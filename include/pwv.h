@@ -72,7 +72,7 @@ typedef struct pwv_hparams {
   int32_t n_mels;                 /* signal.n_mels                                             */
   int32_t hop_length;             /* signal.hop_length                                         */
   int32_t use_biases;             /* model.use_biases                                          */
-  int32_t use_skip_connection;    /* model.use_skip_connection; only 0 is implemented          */
+  int32_t use_skip_connection;    /* model.use_skip_connection; 1 needs precision PWV_PREC_FP32  */
   int32_t precision;              /* PWV_PREC_*                                                */
   int32_t n_layers[PWV_MAX_FLOWS];                     /* len(model.dilations[i])              */
   int32_t dilations[PWV_MAX_FLOWS][PWV_MAX_LAYERS];    /* model.dilations[i][j]                */

@@ -177,6 +177,7 @@ static int configure_simt_kernels() {
   PWV_CUDA(cudaFuncSetAttribute(pwv::k_cond_gemm<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  PWV_CUDA(cudaFuncSetAttribute(pwv::k_skip_simt<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   return PWV_OK;
 }
 static int configure_kernels(const pwv_model* m) {
@@ -221,7 +222,8 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
     return fail(PWV_EINVAL, "skip_channels (%d) must equal 2*residual_channels (%d)", hp->skip_channels, 2 * hp->residual_channels);
   const int C = hp->residual_channels;
   if (C != 64 && C != 128 && C != 256) return fail(PWV_EINVAL, "residual_channels=%d: supported 64, 128, 256", C);
-  if (hp->use_skip_connection) return fail(PWV_EINVAL, "use_skip_connection=True is not implemented on the B200 path");
+  if (hp->use_skip_connection && hp->precision != PWV_PREC_FP32)
+    return fail(PWV_EINVAL, "use_skip_connection=True is implemented on the fp32 path only (precision fp32), not on the tensor-core kernels");
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
   if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_F16X3 && hp->precision != PWV_PREC_BF16)
@@ -453,6 +455,8 @@ struct Workspace {
   float* act[2];    // ping/pong, each [2][N][T][C]
   float* ss;        // [2][N][T] scale, shift
   float* x[2];      // [N][T] ping/pong
+  float* zbuf;      // use_skip_connection: [2][N][T][C] gate output of the current layer
+  float* skip;      // use_skip_connection: [2][N][T][2C] running sum of the skip outputs
   size_t bytes;
 };
 
@@ -471,6 +475,11 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   w->ss = (float*)take(sizeof(float) * (size_t)2 * N * T);
   w->x[0] = (float*)take(sizeof(float) * (size_t)N * T);
   w->x[1] = (float*)take(sizeof(float) * (size_t)N * T);
+  w->zbuf = w->skip = nullptr;
+  if (m->hp.use_skip_connection) {
+    w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
+    w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
+  }
   w->bytes = off;
 }
 
@@ -528,12 +537,25 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
       p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
     }
     p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
-    p.mode = (j == L - 1) ? 1 : 0;
+    p.mode = (j == L - 1) ? 1 : (hp.use_skip_connection ? 2 : 0);
+    p.z_out = w.zbuf;
     PWV_PROF_MARK(m, st);
     pwv::k_layer_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
     PWV_PROF_MARK(m, st);
     ++*launches;
     cur ^= 1;
+    if (hp.use_skip_connection) {     // skip_sum (+)= z_j . Ws_j + bs_j, in layer order (reference modules.py:147)
+      pwv::SkipParams sp;
+      sp.z = (j == L - 1) ? w.act[cur] : w.zbuf;
+      for (int b = 0; b < 2; ++b) {
+        const LayerOff& lo = m->bodies[flow * 2 + b].layers[j];
+        sp.ws[b] = m->d_arena + lo.ws;
+        sp.bs[b] = m->d_arena + lo.bs;
+      }
+      sp.skip_sum = w.skip; sp.N = N; sp.T = T; sp.first = j == 0 ? 1 : 0;
+      pwv::k_skip_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(sp);
+      ++*launches;
+    }
     if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
       PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * N * T * C,
                                sizeof(float) * (size_t)N * T * C, cudaMemcpyDeviceToDevice, st));
@@ -549,6 +571,7 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
     q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
   }
   q.y = w.ss; q.N = N; q.T = T;
+  q.skip_sum = hp.use_skip_connection ? w.skip : nullptr;
   pwv::k_post_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(q);
   ++*launches;
   *cur_buf = cur;

@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_cond_gemm(const float* __res
 //                                                 unless it is the last layer)
 //   mode 1: out[t] = z                           (last layer: its dense_output is dead, the
 //                                                 post-net kernel consumes z)
+//   mode 2: mode 0 + z_out[t] = z                (use_skip_connection: every layer's skip output
+//                                                 is needed, k_skip_simt consumes z)
 // grid = (ceil(T/TM), N, 2 bodies)
 // ------------------------------------------------------------------------------------------------
 struct LayerParams {
@@ -304,6 +306,7 @@ struct LayerParams {
   const float* wd[2];     // [C][C]
   const float* bd[2];     // [C]
   const float* cbias[2];  // [N][t_mel][2C]
+  float* z_out;           // [2][N][T][C], mode 2 only
   int N, T, t_mel, hop, dilation, mode;
 };
 
@@ -362,6 +365,8 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_layer_simt(LayerParams p) {
       if (t0 + m < p.T) *reinterpret_cast<float4*>(xout + (size_t)(t0 + m) * C + 4 * tx) = z;
     } else {
       *reinterpret_cast<float4*>(Zs + (size_t)m * LDZ + 4 * tx) = z;
+      if (p.mode == 2 && t0 + m < p.T)
+        *reinterpret_cast<float4*>(p.z_out + body * body_stride + ((size_t)n * p.T + t0 + m) * C + 4 * tx) = z;
     }
   }
   if (p.mode == 1) return;
@@ -390,6 +395,66 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_layer_simt(LayerParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// use_skip_connection (reference modules.py:147: total = sum(outputs)): after every gated layer
+//   skip_sum[t] (+)= z[t] . Ws + bs          (the layer's skip_output, modules.py:243-250)
+// accumulated in layer order, as Python's left-to-right sum does. grid = (ceil(T/TM), N, 2 bodies)
+// ------------------------------------------------------------------------------------------------
+struct SkipParams {
+  const float* z;         // [2][N][T][C]
+  const float* ws[2];     // [C][2C]
+  const float* bs[2];     // [2C]
+  float* skip_sum;        // [2][N][T][2C]
+  int N, T, first;        // first: assign instead of accumulate
+};
+
+template <int C>
+__global__ void __launch_bounds__(TileCfg<C>::NT) k_skip_simt(SkipParams p) {
+  using Cfg = TileCfg<C>;
+  constexpr int TM = Cfg::TM, NTX = Cfg::NTX, NTY = Cfg::NTY, NT = Cfg::NT, LDA = Cfg::LDA;
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = smem + TM * LDA;
+  const int body = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * TM;
+  const int tx = threadIdx.x % NTX, ty = threadIdx.x / NTX;
+  const float* __restrict__ zin = p.z + ((size_t)body * p.N + n) * p.T * C;
+  float* __restrict__ sk = p.skip_sum + ((size_t)body * p.N + n) * p.T * 2 * C;
+  constexpr int LDZ = C + 4;
+  {
+    constexpr int V = C / 4;
+    for (int e = threadIdx.x; e < TM * V; e += NT) {
+      const int m = e / V, v = e % V;
+      const bool ok = t0 + m < p.T;
+      cp_async16(As + (size_t)m * LDZ + v * 4, zin + (size_t)(ok ? t0 + m : 0) * C + v * 4, ok);
+    }
+    cp_async_commit();
+  }
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  tile_gemm<NTX, NTY, 8>(As, LDZ, C, p.ws[body], 2 * C, Bs, acc);
+  const float4 ba = *reinterpret_cast<const float4*>(p.bs[body] + 4 * tx);
+  const float4 bb = *reinterpret_cast<const float4*>(p.bs[body] + C + 4 * tx);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = t0 + ty + NTY * i;
+    if (t >= p.T) continue;
+    float4* pa = reinterpret_cast<float4*>(sk + (size_t)t * 2 * C + 4 * tx);
+    float4* pb = reinterpret_cast<float4*>(sk + (size_t)t * 2 * C + C + 4 * tx);
+    float4 u = make_float4(acc[i][0] + ba.x, acc[i][1] + ba.y, acc[i][2] + ba.z, acc[i][3] + ba.w);
+    float4 v = make_float4(acc[i][4] + bb.x, acc[i][5] + bb.y, acc[i][6] + bb.z, acc[i][7] + bb.w);
+    if (!p.first) {
+      const float4 su = *pa, sv = *pb;
+      u.x += su.x; u.y += su.y; u.z += su.z; u.w += su.w;
+      v.x += sv.x; v.y += sv.y; v.z += sv.z; v.w += sv.w;
+    }
+    *pa = u;
+    *pb = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Post-net of a body (reference modules.py:145-165 with use_skip_connection False):
 //   skip = z . Ws + bs ; h = relu(skip) . W1 + b1 ; y = relu(h) . W2 + b2      (S = 2C)
 // z is the last layer's gate output. The final 2C -> 1 contraction is a warp-shuffle reduction
@@ -404,6 +469,7 @@ struct PostParams {
   const float* w2[2];     // [2C]
   const float* b2[2];     // [1]
   float* y;               // [2][N][T]   (body 0 = scale, body 1 = shift)
+  const float* skip_sum;  // use_skip_connection: [2][N][T][2C] = sum over layers of (z . Ws + bs); z / ws / bs unused
   int N, T;
 };
 
@@ -417,28 +483,38 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_post_simt(PostParams p) {
   __shared__ float ysum[TM];
   const int body = blockIdx.z, n = blockIdx.y, t0 = blockIdx.x * TM;
   const int tx = threadIdx.x % NTX, ty = threadIdx.x / NTX;
-  const float* __restrict__ zin = p.z + ((size_t)body * p.N + n) * p.T * C;
   constexpr int LDZ = C + 4;
-  {
-    constexpr int V = C / 4;
-    for (int e = threadIdx.x; e < TM * V; e += NT) {
-      const int m = e / V, v = e % V;
-      const bool ok = t0 + m < p.T;
-      cp_async16(As + (size_t)m * LDZ + v * 4, zin + (size_t)(ok ? t0 + m : 0) * C + v * 4, ok);
-    }
-    cp_async_commit();
-  }
   if (threadIdx.x < TM) ysum[threadIdx.x] = 0.f;
-
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  tile_gemm<NTX, NTY, 8>(As, LDZ, C, p.ws[body], 2 * C, Bs, acc);
+  if (p.skip_sum) {
+    // h0 = relu(sum of the layers' skip outputs), straight into the A tile of the postprocess1 GEMM
+    const float* __restrict__ sk = p.skip_sum + ((size_t)body * p.N + n) * p.T * 2 * C;
+    constexpr int V = 2 * C / 4;
+    for (int e = threadIdx.x; e < TM * V; e += NT) {
+      const int m = e / V, v = e % V;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t0 + m < p.T) u = *reinterpret_cast<const float4*>(sk + (size_t)(t0 + m) * 2 * C + v * 4);
+      u.x = fmaxf(u.x, 0.f); u.y = fmaxf(u.y, 0.f); u.z = fmaxf(u.z, 0.f); u.w = fmaxf(u.w, 0.f);
+      *reinterpret_cast<float4*>(As + (size_t)m * LDA + v * 4) = u;
+    }
+  } else {
+    const float* __restrict__ zin = p.z + ((size_t)body * p.N + n) * p.T * C;
+    {
+      constexpr int V = C / 4;
+      for (int e = threadIdx.x; e < TM * V; e += NT) {
+        const int m = e / V, v = e % V;
+        const bool ok = t0 + m < p.T;
+        cp_async16(As + (size_t)m * LDZ + v * 4, zin + (size_t)(ok ? t0 + m : 0) * C + v * 4, ok);
+      }
+      cp_async_commit();
+    }
+    tile_gemm<NTX, NTY, 8>(As, LDZ, C, p.ws[body], 2 * C, Bs, acc);
 
-  // h0 = relu(skip) -> shared (the z tile is dead: tile_gemm ended with a barrier)
-  {
+    // h0 = relu(skip) -> shared (the z tile is dead: tile_gemm ended with a barrier)
     const float4 ba = *reinterpret_cast<const float4*>(p.bs[body] + 4 * tx);
     const float4 bb = *reinterpret_cast<const float4*>(p.bs[body] + C + 4 * tx);
 #pragma unroll

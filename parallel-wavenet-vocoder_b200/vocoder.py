@@ -35,10 +35,11 @@ def _assert_supported(hp):
 
 
 def resolve_precision(dims, precision):
-    """'auto' -> 'f16x3' (tcgen05, fp32-level parity) when the tensor-core kernels cover the channel
-    count (R = D = 64, S = 128), else the exact fp32 FFMA kernels."""
+    """'auto' -> 'f16x3' (tcgen05, fp32-level parity) when the tensor-core kernels cover the graph
+    (R = D = 64, S = 128, no skip connections), else the exact fp32 FFMA kernels."""
     if precision in (None, '', 'auto'):
-        return 'f16x3' if (dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128) else 'fp32'
+        tc_ok = dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128 and not dims['use_skip']
+        return 'f16x3' if tc_ok else 'fp32'
     return precision
 
 

@@ -28,10 +28,12 @@ PKG = 'parallel-wavenet-vocoder_b200'
 
 def import_reference():
     """Import the reference's hparam/models modules under the TF stand-in."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf_shim'))
-    sys.path.insert(0, REF)
-    if ROOT not in sys.path:
-        sys.path.insert(0, ROOT)
+    # search order: the reference first (its hparam.py / models.py / modules.py must win over this
+    # repo's root-level drop-ins of the same names), then the TF stand-in, then this repo
+    for path in (ROOT, os.path.join(ROOT, 'oracle', 'tf_shim'), REF):
+        if path in sys.path:
+            sys.path.remove(path)
+        sys.path.insert(0, path)
     import tensorflow as tf                      # the shim
     real_load_all = yaml.load_all
     yaml.load_all = lambda stream, Loader=None: real_load_all(stream, Loader=yaml.SafeLoader)
@@ -111,6 +113,17 @@ def main():
     print('2-flow graph : reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (err, np.abs(wav).max()))
     assert err < 1e-12
     np.savez_compressed(os.path.join(HERE, 'ref_flows.npz'), **pack(noise, mel, wav, weights, dil, (43, 0.2, 2.0)))
+
+    # ---- fixture 3: the same 2-flow graph with use_skip_connection=True (reference modules.py:147)
+    ref_hp.model.use_skip_connection = True
+    weights = W.init_weights(my_hp, seed=44, bias_std=0.1, dtype=np.float32)
+    wav, created = run_reference(tf, ref_models, weights, noise, mel)
+    ours = O.iaf_vocoder_forward(noise, mel, weights, dil, hop, use_skip_connection=True, dtype=np.float64)
+    err = np.abs(ours - wav).max()
+    print('skip-sum graph: reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (err, np.abs(wav).max()))
+    assert err < 1e-12
+    np.savez_compressed(os.path.join(HERE, 'ref_skip.npz'), **pack(noise, mel, wav, weights, dil, (44, 0.1, 1.0)))
+    ref_hp.model.use_skip_connection = False
     print('wrote ref_small.npz, ref_flows.npz, ref_varlist.txt (%d variables in the default graph)' % len(W.variable_shapes(my_hp.set_hparam_yaml('default'))))
 
 

@@ -64,8 +64,11 @@ def test_model_create_validates(hp):
     _, _, rc = _create(hp)
     assert rc == -1 and b'filter_width' in lib.pwv_last_error()
     hp.model.filter_width = 2
-    hp.model.use_skip_connection = True
-    _, _, rc = _create(hp)
+    hp.model.use_skip_connection = True                 # fp32 path only
+    _, h2, rc = _create(hp, 'fp32')
+    assert rc == 0
+    lib.pwv_model_destroy(h2)
+    _, _, rc = _create(hp, 'f16x3')
     assert rc == -1 and b'use_skip_connection' in lib.pwv_last_error()
     hp.model.use_skip_connection = False
     hp.model.residual_channels = 48

@@ -188,3 +188,21 @@ def test_other_conditioning_widths(hp, n_mels, cc, precision):
     ref = _oracle(hp, weights, noise, mel)
     out, _ = _run(hp, weights, noise, mel)
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize('channels', [64, 128])
+def test_use_skip_connection(hp, channels):
+    """model.use_skip_connection=True (reference modules.py:147: the post-net sees the SUM of every
+    layer's skip output); fp32 path, which 'auto' selects for it."""
+    small_case(hp, channels=channels, dilations=((1, 2, 4, 512), (1, 8)), t=800, precision='auto')
+    hp.model.use_skip_connection = True
+    weights = pkg('weights').init_weights(hp, seed=13, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(2, 800, 80, 80)
+    d = pkg('weights').model_dims(hp)
+    ref = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], True, True, dtype=np.float64)
+    out, model = _run(hp, weights, noise, mel)
+    assert model.precision == 'fp32'
+    assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+    hp.model.use_skip_connection = False
+    ref_noskip = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], True, False, dtype=np.float64)
+    assert np.abs(ref - ref_noskip).max() > 1e-3           # the option really changes the result

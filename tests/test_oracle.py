@@ -9,14 +9,15 @@ from conftest import ROOT, load_golden, pkg, small_case
 from oracle import iaf_oracle as O
 
 
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz'])
 def test_oracle_reproduces_reference_golden(hp, name):
     weights, noise, mel, wav, dil = load_golden(hp, name)
+    skip = name == 'ref_skip.npz'        # generated with model.use_skip_connection=True
     if name == 'ref_small.npz':          # keep the CPU suite quick: 1 of the 2 utterances
         noise, mel, wav = noise[:1], mel[:1], wav[:1]
-    got = O.iaf_vocoder_forward(noise, mel, weights, dil, 80, dtype=np.float64)
+    got = O.iaf_vocoder_forward(noise, mel, weights, dil, 80, use_skip_connection=skip, dtype=np.float64)
     assert np.abs(got - wav).max() < 1e-10
-    got32 = O.iaf_vocoder_forward(noise, mel, weights, dil, 80, dtype=np.float32)
+    got32 = O.iaf_vocoder_forward(noise, mel, weights, dil, 80, use_skip_connection=skip, dtype=np.float32)
     assert np.abs(got32 - wav).max() < 1e-4 * max(1.0, np.abs(wav).max())
 
 
