@@ -668,10 +668,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
         }
       }
       // ---- the tile's output sits in the x[t] boxes (my half: 128 rows x 128 B, swizzled). The four warps of
-      //      this (slot, half) copy it out with full-line stores: a warp instruction writes 4 rows x 128 B.
+      //      this (slot, half) copy it out with full-line stores: a warp instruction writes 4 rows x 128 B, and each
+      //      warp copies exactly the 32 rows its own lanes wrote.
       //      (Per-thread row stores and a TMA store were both measured slower: the former issues 32 partial
       //      lines per instruction, the latter holds the boxes ~1.5k cycles while the TMA unit drains them.)
-      named_bar_sync(1 + slot * 2 + half, 128);
+      __syncwarp();     // rows 32*quarter .. +31 of the box were written by this warp's own lanes: no wider barrier needed
       {
         uint8_t* box = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES;
         const int t_first = (tile % p.tiles_per_utt) * TC_TM;

@@ -206,3 +206,30 @@ def test_use_skip_connection(hp, channels):
     hp.model.use_skip_connection = False
     ref_noskip = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], True, False, dtype=np.float64)
     assert np.abs(ref - ref_noskip).max() > 1e-3           # the option really changes the result
+
+
+@pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
+def test_properties_at_c3_size(hp, precision):
+    """BASELINE config c3 (N=64, T=96000 @ 24 kHz: 6.1 M samples, 3.1 GB of activations per buffer --
+    far beyond L2): determinism, batch independence and causality, bit for bit; the ragged tile
+    (96000 = 750 * 128 exactly, so a 95920-sample run covers the partial-tile path at size)."""
+    hp.set_hparam_yaml('bench/c3')
+    W = pkg('weights')
+    weights = W.init_weights(hp, seed=0, bias_std=0.05)
+    for n, t in ((64, 96000), (3, 95920)):
+        noise, mel = O.synthetic_inputs(n, t, 80, 80)
+        out, model = _run(hp, weights, noise, mel, precision=precision)
+        out = out.cpu().numpy()
+        assert np.isfinite(out).all()
+        dn, dm = torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()
+        assert np.array_equal(model.forward(dn, dm).cpu().numpy(), out)
+        k = n - 2
+        assert np.array_equal(model.forward(dn[k:k + 1], dm[k:k + 1]).cpu().numpy()[0], out[k])
+        t0 = 50000
+        noise2, mel2 = noise.copy(), mel.copy()
+        noise2[:, t0:] -= 0.5
+        mel2[:, (t0 + 40) // 80 + 1:, :] *= 0.5
+        out2 = model.forward(torch.from_numpy(noise2).cuda(), torch.from_numpy(mel2).cuda()).cpu().numpy()
+        assert np.array_equal(out2[:, :t0], out[:, :t0]) and not np.array_equal(out2[:, t0:], out[:, t0:])
+        del model, dn, dm
+        torch.cuda.empty_cache()
