@@ -232,11 +232,14 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default=None, help="override engine.precision: fp32 | f16x3 | bf16")
+    ap.add_argument('--tc-variant', type=int, default=None, help='gated-layer kernel variant (PWV_TC_VARIANT: 0 | 1 | 2), A/B runs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
+    if args.tc_variant is not None:
+        os.environ['PWV_TC_VARIANT'] = str(args.tc_variant)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -317,16 +320,24 @@ def main():
 
     # ---- roofline of the dominant kernel (gated dilated layer), separate profiled steps
     pk = peaks()
-    model.set_profiling(True)
-    layer_ms, layer_n, fwd_ms = [], 0, []
-    for _ in range(3):
-        flush.fill_(1)
-        model.forward(noise, mel, out=out)
-        lm, ln, fm = model.profile_read()
-        layer_ms.append(lm); layer_n = ln; fwd_ms.append(fm)
-    model.set_profiling(False)
-    # One launch of the gated-layer kernel runs all layers of a flow (both bodies); the algorithmic bytes
-    # are per layer: each body reads its 64-channel fp32 input once and writes its output once.
+
+    def profiled(mode):
+        model.set_profiling(mode)
+        lms, ln, fms = [], 0, []
+        for _ in range(3):
+            flush.fill_(1)
+            model.forward(noise, mel, out=out)
+            lm, ln, fm = model.profile_read()
+            lms.append(lm); fms.append(fm)
+        model.set_profiling(False)
+        return lms, ln, fms
+    # mode 2: one event pair around each flow's chain of gated-layer launches, launched as in the timed steps
+    # (programmatic dependent launch on) -> the kernel's average launch duration inside the step;
+    # mode 1: every launch bracketed (serialised) -> the isolated launch duration, what ncu's list shows
+    layer_ms, layer_n, fwd_ms = profiled(2)
+    iso_ms, iso_n, _ = profiled(1)
+    # One launch of the gated-layer kernel runs one layer of both bodies; the algorithmic bytes per launch:
+    # each body reads its 64-channel fp32 input once and writes its output once.
     n_gated = sum(len(d) for d in dims['dilations'])                     # gated layers per forward (x 2 bodies each)
     bytes_per_layer = 2 * n * t * (2 * dims['R'] * 4)
     layer_s = float(np.median(layer_ms)) * 1e-3                          # device time of all gated-layer launches
@@ -338,12 +349,16 @@ def main():
         with open(tpath) as fh:
             traffic = json.load(fh).get(precision, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
-                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layers (tcgen05 flow kernel, both bodies)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
+                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layer k_layer_tc (tcgen05, both bodies per launch)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
                 'bytes_per_launch': n_gated * bytes_per_layer / max(layer_n, 1), 'avg_launch_us': layer_s * 1e6 / max(layer_n, 1),
+                'isolated_launch_us': float(np.median(iso_ms)) * 1e3 / max(iso_n, 1),
+                'frac_isolated': n_gated * bytes_per_layer / (float(np.median(iso_ms)) * 1e-3) / 1e9 / pk['hbm'],
                 'launches_per_step': layer_n, 'gated_layers_per_step': n_gated, 'us_per_layer': layer_s * 1e6 / n_gated,
                 'share_of_step': float(np.median(layer_ms) / np.median(fwd_ms)),
                 'tflops_fp32_equiv': 2 * n_gated * mac_per_layer / layer_s / 1e12,
-                'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); the kernel is bound by tensor/MUFU/issue, not HBM: see DESIGN.md'}
+                'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); avg_launch_us = CUDA events around each flow\'s chain of '
+                        'gated-layer launches as launched in the timed steps / launches; isolated_launch_us = every launch bracketed (serialised, what ncu lists); '
+                        'the kernel is bound by tensor/MUFU/issue, not HBM: see DESIGN.md'}
 
     # ---- e2e: host buffers in, host buffer out, copies inside the timed region.
     #      N = 1: the C-ABI call pwv_forward_host (H2D + kernels + D2H + sync inside the call).
@@ -417,6 +432,7 @@ def main():
             'dtype': {'fp32': 'f32', 'f16x3': 'f32 (fp16 hi/lo 3-term tensor-core split, fp32 accumulate)', 'bf16': 'bf16'}[precision],
             'data': 'synthetic',
             'config': {'workload': WORKLOADS[args.workload][1], 'per_gpu_batch': n, 'length': t, 'precision': precision,
+                       'tc_variant': os.environ.get('PWV_TC_VARIANT', 'default'),
                        'l2': 'flushed (256 MB write) before every timed step', 'timing': 'CUDA events per step, max over ranks'},
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }

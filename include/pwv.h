@@ -123,10 +123,13 @@ int pwv_forward_host(pwv_model* m, const float* noise, const float* mel, float* 
 /* Kernel launches enqueued by the most recent pwv_forward on this model (for bench accounting). */
 int pwv_last_launch_count(const pwv_model* m);
 
-/* Per-kernel timing for the roofline report. While enabled, pwv_forward brackets every gated-layer
- * kernel launch (the dominant kernel) with CUDA events on `stream`. pwv_profile_read waits for the
- * most recent forward and returns the summed device time of those launches, their count, and the
- * device time of the whole forward. */
+/* Per-kernel timing for the roofline report. enable = 1: pwv_forward brackets EVERY gated-layer kernel
+ * launch (the dominant kernel) with CUDA events on `stream`; the events serialise the launches, so the
+ * programmatic-dependent-launch overlap of production runs is off and each launch is timed in isolation.
+ * enable = 2: one event pair around each flow's chain of gated-layer launches, launched exactly as in
+ * production (overlap on); the average launch duration is chain time / launches. pwv_profile_read waits
+ * for the most recent forward and returns the summed device time of the bracketed launches, their count,
+ * and the device time of the whole forward. 0 switches profiling off. */
 int pwv_set_profiling(pwv_model* m, int enable);
 /* Debug: device buffer of 4*16*16 int64 that CTA 0 fills with clock64() stamps of its phases while it
  * runs ONE gated layer on the tensor cores (NULL switches it off). `layer_index` counts the gated

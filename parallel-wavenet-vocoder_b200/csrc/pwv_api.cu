@@ -64,6 +64,10 @@ struct BodyOff {
   size_t w1, b1, w2, b2;
 };
 
+#ifndef PWV_TC_VARIANT_DEFAULT
+#define PWV_TC_VARIANT_DEFAULT 0
+#endif
+
 struct pwv_model {
   pwv_hparams hp;
   int C, S, Cc;
@@ -97,10 +101,13 @@ struct pwv_model {
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
   bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
+  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1|2 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
-  bool profiling = false;
-  std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then pairs per layer launch
+  int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
+                                 // 2: one pair around each flow's chain of gated-layer launches (as in production)
+  std::vector<cudaEvent_t> ev;   // [0],[1] = whole forward; then the pairs
   int ev_used = 0;
+  int prof_launches = 0;         // gated-layer launches covered by the pairs
 };
 
 static cudaEvent_t prof_event(pwv_model* m) {
@@ -186,6 +193,10 @@ static int configure_kernels(const pwv_model* m) {
   if (m->hp.precision != PWV_PREC_FP32) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -247,6 +258,10 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->total_layers = total;
   m->max_layers = mx;
   m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
+  if (const char* v = getenv("PWV_TC_VARIANT")) {
+    const int k = atoi(v);
+    if (k >= 0 && k <= 2) m->tc_variant = k;
+  }
   build_var_list(m);
   *out = m;
   return PWV_OK;
@@ -612,7 +627,11 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   const pwv_hparams& hp = m->hp;
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
   const bool bf16 = hp.precision == PWV_PREC_BF16;
+  // layer-kernel variant (PWV_TC_VARIANT, read at pwv_model_create): 0 = 8 worker warps per tile slot, scalar
+  // epilogue arithmetic; 1 = the same with packed fp32x2 arithmetic; 2 = all 16 worker warps on both slots + packed
   auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
+  if (m->tc_variant == 1) kern = bf16 ? pwv::k_layer_tc<true, false, true> : pwv::k_layer_tc<false, true, true>;
+  if (m->tc_variant == 2) kern = bf16 ? pwv::k_layer_tc<true, false, true, true> : pwv::k_layer_tc<false, true, true, true>;
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
   const int tiles_body = N * tiles_per_utt;
   int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;
@@ -633,7 +652,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     p.tiles_per_utt = tiles_per_utt;
     p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
     p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
-    PWV_PROF_MARK(m, st);
+    if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
     {
       // programmatic dependent launch: this layer's prologue overlaps the previous kernel's tail
       // (not while profiling: the events between the launches would serialise them anyway)
@@ -646,10 +665,11 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = (m->profiling || !m->use_pdl) ? 0 : 1;
+      cfg.numAttrs = (m->profiling == 1 || !m->use_pdl) ? 0 : 1;
       PWV_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[cur], p));
     }
-    PWV_PROF_MARK(m, st);
+    if (m->profiling == 1 || (m->profiling == 2 && j == L - 1)) PWV_PROF_MARK(m, st);
+    if (m->profiling) ++m->prof_launches;
     ++*launches;
     cur ^= 1;
     if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
@@ -686,6 +706,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   cudaStream_t st = (cudaStream_t)stream;
   int launches = 0;
   m->ev_used = 0;
+  m->prof_launches = 0;
   PWV_PROF_MARK(m, st);   // [0] forward start
   PWV_PROF_MARK(m, st);   // [1] placeholder, re-recorded at the end
 
@@ -827,7 +848,7 @@ int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int launch_index
 
 int pwv_set_profiling(pwv_model* m, int enable) {
   if (!m) return fail(PWV_EINVAL, "null model");
-  m->profiling = enable != 0;
+  m->profiling = enable == 2 ? 2 : (enable != 0 ? 1 : 0);
   m->ev_used = 0;
   return PWV_OK;
 }
@@ -847,7 +868,7 @@ int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double
     ++n;
   }
   if (layer_ms) *layer_ms = sum;
-  if (layer_launches) *layer_launches = n;
+  if (layer_launches) *layer_launches = m->prof_launches > 0 ? m->prof_launches : n;
   return PWV_OK;
 }
 

@@ -145,7 +145,9 @@ class PwvModel:
         return _lib.check(self.lib.pwv_last_launch_count(self._h))
 
     def set_profiling(self, enable):
-        _lib.check(self.lib.pwv_set_profiling(self._h, int(bool(enable))))
+        """0 / False: off; 1 / True: every gated-layer launch timed in isolation; 2: each flow's chain of
+        gated-layer launches timed as launched in production (include/pwv.h)."""
+        _lib.check(self.lib.pwv_set_profiling(self._h, 2 if enable == 2 else int(bool(enable))))
 
     def profile_read(self):
         """-> (summed ms of the gated-layer launches, their count, ms of the whole forward)."""

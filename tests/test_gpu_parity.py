@@ -233,3 +233,35 @@ def test_properties_at_c3_size(hp, precision):
         assert np.array_equal(out2[:, :t0], out[:, :t0]) and not np.array_equal(out2[:, t0:], out[:, t0:])
         del model, dn, dm
         torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
+@pytest.mark.parametrize('variant', [1, 2])
+def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision):
+    """The gated-layer kernel variants (PWV_TC_VARIANT: 1 = packed fp32x2 epilogue arithmetic, 2 = all 16
+    worker warps on both tile slots + packed) perform the same IEEE operations per element as variant 0, so
+    their outputs must be BIT-identical to it -- on the default graph, on ragged / d >= T edge shapes and on a
+    one-tile-per-CTA-slot case -- and (f16x3) within TOL of the oracle."""
+    W = pkg('weights')
+    cases = [('default', None, 2, 4000), ('edge', ((1, 512, 2), (256, 1)), 5, 1040), ('edge', ((1, 512, 2), (256, 1)), 1, 80),
+             ('default', None, 8, 16000)]
+    for kind, dil, n, t in cases:
+        if kind == 'edge':
+            small_case(hp, dilations=dil, n=n, t=t, precision=precision)
+        else:
+            hp.set_hparam_yaml('default')
+            hp.engine.precision = precision
+        weights = W.init_weights(hp, seed=2, bias_std=0.1)
+        noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=21, noise_seed=22)
+        monkeypatch.setenv('PWV_TC_VARIANT', '0')
+        base, _ = _run(hp, weights, noise, mel, precision=precision)
+        monkeypatch.setenv('PWV_TC_VARIANT', str(variant))
+        got, model = _run(hp, weights, noise, mel, precision=precision)
+        again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
+        assert torch.equal(got, again), (kind, n, t, 'not deterministic')
+        assert torch.equal(got, base), (kind, n, t, float((got - base).abs().max()))
+        if precision == 'f16x3' and n * t <= 8000:
+            ref = _oracle(hp, weights, noise, mel)
+            assert np.abs(got.cpu().numpy() - ref).max() <= TOL
+        del model

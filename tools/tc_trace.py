@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Print the phase timeline (clock64 deltas) of CTA 0 of one tensor-core gated-layer launch.
-usage: tc_trace.py [precision] [layer_index]   (default f16x3, layer 2 of flow 0, d=4)"""
+usage: tc_trace.py [precision] [layer_index]   (default f16x3, layer 2 of flow 0, d=4)
+The kernel variant follows PWV_TC_VARIANT (variant 2 stamps x_landed/a_ready/d1_ready/z_ready/d2_ready/out_ready
+of both slots from warp 0, which serves both)."""
 import ctypes, importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,13 +28,13 @@ L.check(m.lib.pwv_debug_set_trace(m._h, None, -1))
 t = buf.cpu().numpy().reshape(4, 16, 16)
 base = t[t > 0].min()
 names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_ready']
-print(f'precision {prec}, gated layer {launch}; cycles since the first stamp (delta from the previous event)')
+print(f'precision {prec}, variant {os.environ.get("PWV_TC_VARIANT", "default")}, gated layer {launch}; cycles since the first stamp (delta from the previous event)')
 for role in (0, 1):
     print(f'--- worker slot {role}')
     for j in range(8):
         row = t[role, j]
-        if row[0] == 0: break
-        s, prev = [], row[0]
+        if not row.any(): break
+        s, prev = [], row[row > 0].min()
         for k, nm in enumerate(names):
             if row[k] == 0: continue
             s.append(f'{nm}={row[k]-base}(+{row[k]-prev})')
