@@ -101,7 +101,7 @@ struct pwv_model {
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
   bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
-  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1|2 in the environment overrides (A/B runs)
+  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0..3 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
                                  // 2: one pair around each flow's chain of gated-layer launches (as in production)
@@ -195,6 +195,8 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
@@ -260,7 +262,7 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
   if (const char* v = getenv("PWV_TC_VARIANT")) {
     const int k = atoi(v);
-    if (k >= 0 && k <= 2) m->tc_variant = k;
+    if (k >= 0 && k <= 3) m->tc_variant = k;
   }
   build_var_list(m);
   *out = m;
@@ -628,10 +630,13 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
   const bool bf16 = hp.precision == PWV_PREC_BF16;
   // layer-kernel variant (PWV_TC_VARIANT, read at pwv_model_create): 0 = 8 worker warps per tile slot, scalar
-  // epilogue arithmetic; 1 = the same with packed fp32x2 arithmetic; 2 = all 16 worker warps on both slots + packed
+  // epilogue arithmetic; 1 = the same with packed fp32x2 arithmetic; 2 = all 16 worker warps on both slots + packed;
+  // 3 = k_layer_tc3: 1024 threads, 16 worker warps per slot, MMA / TMA issue folded into the slots' first warps
   auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
   if (m->tc_variant == 1) kern = bf16 ? pwv::k_layer_tc<true, false, true> : pwv::k_layer_tc<false, true, true>;
   if (m->tc_variant == 2) kern = bf16 ? pwv::k_layer_tc<true, false, true, true> : pwv::k_layer_tc<false, true, true, true>;
+  if (m->tc_variant == 3) kern = bf16 ? pwv::k_layer_tc3<true, false> : pwv::k_layer_tc3<false, true>;
+  const int block = m->tc_variant == 3 ? pwv::TC3_THREADS : pwv::TC_THREADS;
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
   const int tiles_body = N * tiles_per_utt;
   int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;
@@ -658,7 +663,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       // (not while profiling: the events between the launches would serialise them anyway)
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(pwv::TC_THREADS);
+      cfg.blockDim = dim3(block);
       cfg.dynamicSmemBytes = pwv::TC_SMEM_BYTES;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
