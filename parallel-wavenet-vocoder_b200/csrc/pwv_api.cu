@@ -101,7 +101,8 @@ struct pwv_model {
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
   bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
-  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0..3 in the environment overrides (A/B runs)
+  bool use_flags = true;         // tile handshake between consecutive gated layers (PWV_NO_TILE_FLAGS=1: off)
+  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
                                  // 2: one pair around each flow's chain of gated-layer launches (as in production)
@@ -195,10 +196,6 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -260,9 +257,10 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->total_layers = total;
   m->max_layers = mx;
   m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
+  m->use_flags = getenv("PWV_NO_TILE_FLAGS") == nullptr && m->use_pdl;
   if (const char* v = getenv("PWV_TC_VARIANT")) {
     const int k = atoi(v);
-    if (k >= 0 && k <= 3) m->tc_variant = k;
+    if (k >= 0 && k <= 1) m->tc_variant = k;
   }
   build_var_list(m);
   *out = m;
@@ -474,6 +472,8 @@ struct Workspace {
   float* x[2];      // [N][T] ping/pong
   float* zbuf;      // use_skip_connection: [2][N][T][C] gate output of the current layer
   float* skip;      // use_skip_connection: [2][N][T][2C] running sum of the skip outputs
+  int* flags;       // tensor-core path: [total gated layers][2][N * ceil(T/128)] per-tile "output stored" flags
+  size_t flags_bytes;
   size_t bytes;
 };
 
@@ -496,6 +496,13 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   if (m->hp.use_skip_connection) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
     w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
+  }
+  w->flags = nullptr;
+  w->flags_bytes = 0;
+  if (m->hp.precision != PWV_PREC_FP32) {
+    const size_t tiles_body = (size_t)N * ((T + pwv::TC_TM - 1) / pwv::TC_TM);
+    w->flags_bytes = sizeof(int) * (size_t)m->total_layers * 2 * tiles_body;
+    w->flags = (int*)take(w->flags_bytes);
   }
   w->bytes = off;
 }
@@ -629,14 +636,12 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   const pwv_hparams& hp = m->hp;
   const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
   const bool bf16 = hp.precision == PWV_PREC_BF16;
-  // layer-kernel variant (PWV_TC_VARIANT, read at pwv_model_create): 0 = 8 worker warps per tile slot, scalar
-  // epilogue arithmetic; 1 = the same with packed fp32x2 arithmetic; 2 = all 16 worker warps on both slots + packed;
-  // 3 = k_layer_tc3: 1024 threads, 16 worker warps per slot, MMA / TMA issue folded into the slots' first warps
+  // layer-kernel variant (PWV_TC_VARIANT, read at pwv_model_create): 0 = scalar epilogue arithmetic,
+  // 1 = packed fp32x2 epilogue arithmetic (bit-identical). Two more variants were measured and removed
+  // (DESIGN.md 4.1): all 16 worker warps serving both slots in a static phase order, and a 1024-thread kernel.
   auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
   if (m->tc_variant == 1) kern = bf16 ? pwv::k_layer_tc<true, false, true> : pwv::k_layer_tc<false, true, true>;
-  if (m->tc_variant == 2) kern = bf16 ? pwv::k_layer_tc<true, false, true, true> : pwv::k_layer_tc<false, true, true, true>;
-  if (m->tc_variant == 3) kern = bf16 ? pwv::k_layer_tc3<true, false> : pwv::k_layer_tc3<false, true>;
-  const int block = m->tc_variant == 3 ? pwv::TC3_THREADS : pwv::TC_THREADS;
+  const int block = pwv::TC_THREADS;
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
   const int tiles_body = N * tiles_per_utt;
   int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;
@@ -655,6 +660,14 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : 0;
     p.tiles_per_utt = tiles_per_utt;
+    {
+      // tile handshake with the previous gated layer of the flow (see TcLayerParams); the first layer of a flow
+      // follows k_front and waits for it as a whole. PWV_NO_TILE_FLAGS=1 restores whole-kernel waits everywhere.
+      int* fl = w.flags + (layer_base / 2 + (size_t)j) * 2 * tiles_body;
+      p.flags_out = (m->use_flags && j + 1 < L) ? fl : nullptr;
+      p.flags_in = (m->use_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
+      p.prev_dilation = j > 0 ? hp.dilations[flow][j - 1] : 0;
+    }
     p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
     p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
     if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
@@ -714,6 +727,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   m->prof_launches = 0;
   PWV_PROF_MARK(m, st);   // [0] forward start
   PWV_PROF_MARK(m, st);   // [1] placeholder, re-recorded at the end
+  if (w.flags) PWV_CUDA(cudaMemsetAsync(w.flags, 0, w.flags_bytes, st));
 
   // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
   {

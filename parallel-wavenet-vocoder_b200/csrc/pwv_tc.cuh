@@ -250,6 +250,13 @@ struct TcLayerParams {
   int N, T, t_mel, hop, dilation, mode;
   int tiles_per_utt;        // ceil(T / 128)
   int cb_in_smem;           // 1: a tile spans <= TC_CB_FRAMES mel frames, its conditioning rows are staged by TMA
+  // Tile handshake between consecutive gated layers (both kernels resident under programmatic dependent launch):
+  // flags_in  = the previous layer's per-tile "output stored" flags [2 bodies][N * tiles_per_utt], or nullptr:
+  //             wait for the whole previous kernel (griddepcontrol.wait) -- first layer of a flow;
+  // flags_out = this layer's flags (zeroed at the start of the forward), or nullptr.
+  const int* flags_in;
+  int* flags_out;
+  int prev_dilation;        // dilation of the previous layer: its x[t-d] reads of the rows this layer overwrites
   long long* trace;         // debug: [4 roles][16 tiles][16 events] clock64 stamps of CTA 0 (or nullptr)
 };
 
@@ -446,20 +453,6 @@ __device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_
     if (SPLIT) ptx::tmem_st8(taddr_lo + c * 8, lo);
   }
 }
-// 16 staged floats (chunks c0 .. c0+3 of my box row) -> 8 packed hi columns (+ 8 lo)
-template <bool BF16, bool SPLIT, bool PK>
-__device__ __forceinline__ void tc_prep16(uint8_t* box_row, int r, int c0, uint32_t taddr_hi, uint32_t taddr_lo) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const float4 a = *box_chunk(box_row, r, c0 + q * 2), b = *box_chunk(box_row, r, c0 + q * 2 + 1);
-    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    split8x<BF16, SPLIT, PK>(v, hi + q * 4, lo + q * 4);
-  }
-  ptx::tmem_st8(taddr_hi, hi);
-  if (SPLIT) ptx::tmem_st8(taddr_lo, lo);
-}
-
 constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
 constexpr int TC_MMA_WARP = 16;                           // 16, 17: MMA issuer of tile slot 0, 1
 constexpr int TC_TMA_WARP = 18;                           // 18, 19: TMA producer of tile slot 0, 1
@@ -493,9 +486,9 @@ __device__ __forceinline__ void tc_unlock(int* lock) {
   }
 }
 
-// PK: packed fp32x2 epilogue arithmetic. ALL16: all 16 worker warps serve BOTH tile slots, phase by phase in a
-// static order (a thread = one row x 16 channels), instead of 8 warps per slot (see the ALL16 worker section).
-template <bool BF16, bool SPLIT, bool PK = false, bool ALL16 = false>
+// PK: packed fp32x2 epilogue arithmetic (bit-identical results, ~15 % fewer worker instructions, same speed:
+// the worker phases are latency-bound, not issue-bound -- kept selectable for A/B runs).
+template <bool BF16, bool SPLIT, bool PK = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
   using namespace ptx;
@@ -517,7 +510,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
         mbar_init(&bars->x_full[s], 1);
         mbar_init(&bars->y_full[s], 1);
         mbar_init(&bars->c_full[s], 1);
-        constexpr uint32_t NW = ALL16 ? 512 : 256;      // worker threads that serve one tile slot
+        constexpr uint32_t NW = 256;                    // worker threads that serve one tile slot
         mbar_init(&bars->x_free[s], NW);
         mbar_init(&bars->y_free[s], NW);
         mbar_init(&bars->a_ready[s], NW);
@@ -630,7 +623,34 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
         bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
       };
       const int tiles_s = (n_local + 1 - s) / 2;
-      pdl_wait_prior_grid();      // the previous layer's output (and everything before it) is complete
+      // Tile handshake: tile (n, k) of this layer needs the previous layer's tiles k (its x[t] rows) and the one or
+      // two tiles that hold rows t0-d .. t0+127-d; and it overwrites (ping-pong buffers) rows that the previous
+      // layer's tiles k + d'/128 (+1) still read as THEIR x[t-d'] window. All of them processed by CTAs of the
+      // previous kernel, which are running or done (1 CTA per SM: ours got its SM from one of them).
+      auto wait_tiles = [&](int j) {
+        if (!p.flags_in) return;
+        int n, t0;
+        coords(j, n, t0);
+        const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
+        const int* f = p.flags_in + (size_t)body * tiles_body + (size_t)n * p.tiles_per_utt;
+        const int hi = t0 + TC_TM - 1 - p.dilation, lo = max(t0 - p.dilation, 0);
+        const int k1 = hi >= 0 ? lo / TC_TM : k, k2 = hi >= 0 ? hi / TC_TM : k;
+        const int k3 = min(k + p.prev_dilation / TC_TM, last), k4 = min(k + (p.prev_dilation + TC_TM - 1) / TC_TM, last);
+        for (;;) {
+          const int a = ld_relaxed_gpu(f + k), b = ld_relaxed_gpu(f + k1), c = ld_relaxed_gpu(f + k2);
+          const int d = ld_relaxed_gpu(f + k3), e = ld_relaxed_gpu(f + k4);
+          if (a & b & c & d & e) break;
+        }
+        fence_acq_rel_gpu();            // (acquire: the flagged tiles' rows are visible ...)
+        fence_proxy_async_global();     // (... to the TMA loads issued next)
+      };
+      auto signal_tile = [&](int j) {   // after y_free[s]: all 256 workers of the slot have stored the tile's output
+        if (!p.flags_out) return;
+        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+        fence_acq_rel_gpu();            // (release, cumulative over the workers' stores observed through y_free)
+        st_relaxed_gpu(p.flags_out + (size_t)body * tiles_body + tile, 1);
+      };
+      if (!p.flags_in) pdl_wait_prior_grid();      // the previous kernel's output (and everything before it) is complete
       // Slot 1 lets slot 0's first boxes land before asking for its own: the TMA unit moves ~40 B/clk, so
       // interleaving both slots' 64 KB would deliver both at ~4k cycles; this way slot 0 starts at ~2k and
       // the two tiles begin half a phase apart, which is where the ping-pong wants them anyway.
@@ -638,188 +658,41 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
       if (tiles_s > 0) {
         int n, t0;
         coords(0, n, t0);
+        wait_tiles(0);
         issue_x(0);
         mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
         tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
         tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
         issue_c(0);
       }
-      for (int j = 0; j + 1 < tiles_s; ++j) {
-        // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile
-        mbar_wait(&bars->x_free[s], j & 1);
-        issue_x(j + 1);
-        TC_TRACE(3, j, s * 8 + 0);
+      for (int j = 0; j < tiles_s; ++j) {
+        const bool more = j + 1 < tiles_s;
+        if (more) {
+          // the slot's x[t-d] boxes have been converted: refill them for the slot's next tile (whose inputs are
+          // checked here, early in this tile's chain, so that the x[t] refill below never has to wait for them)
+          mbar_wait(&bars->x_free[s], j & 1);
+          wait_tiles(j + 1);
+          issue_x(j + 1);
+          TC_TRACE(3, j, s * 8 + 0);
+        } else if (!p.flags_out) {
+          break;
+        }
         // the workers have copied the tile's output out of the x[t] boxes and are done with the
-        // conditioning rows: refill both for the next tile
+        // conditioning rows: refill both for the next tile, then publish the tile
         mbar_wait(&bars->y_free[s], j & 1);
-        int n, t0;
-        coords(j + 1, n, t0);
-        mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
-        tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
-        tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
-        issue_c(j + 1);
-        TC_TRACE(3, j, s * 8 + 2);
+        if (more) {
+          int n, t0;
+          coords(j + 1, n, t0);
+          mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+          tma_load_3d(st + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[s]);
+          tma_load_3d(st + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[s]);
+          issue_c(j + 1);
+          TC_TRACE(3, j, s * 8 + 2);
+        }
+        signal_tile(j);
       }
     }
     __syncwarp();
-  } else if (ALL16) {
-    // ======================= workers, ALL16 schedule =======================
-    // warp -> (channel quarter cq, lane quarter); thread -> (row of the tile, 16 of the 64 channels), for BOTH
-    // tile slots. The 8-warps-per-slot version leaves a slot's warps idle while its GEMMs run (a 9.3k-cycle
-    // chain per tile, of which 3.5k wait on the tensor pipe) and runs every phase with 2 warps per scheduler;
-    // here every phase of either slot gets all 16 warps (4 per scheduler) and the phases of the two slots
-    // are interleaved in a static order so that a slot's GEMM runs under the other slot's epilogue:
-    //     [Px0 Px1] [E1_0 E1_1] [E2_0 CO_0 E2_1 CO_1] [Py0 Py1]      per pair of tiles
-    // Px / Py = operand prep of the x[t-d] / x[t] boxes (a_ready after Px), E1 = gate, E2 = residual,
-    // CO = copy-out. Py comes first for the next tile (its boxes are refilled after CO, the x[t-d] boxes
-    // long before), so the y refill is covered by the other slot's E2/CO and Py.
-    const int cq = warp >> 2, quarter = warp & 3, half = cq >> 1, sub = cq & 1;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + cq * 16;
-    const float* scal = reinterpret_cast<const float*>(smem + TC_OFF_SCAL);
-    const bool tracer = warp == 0 && lane == 0;
-    float sf = 0.f, sg = 0.f, s2 = 0.f;
-    const int n_slot[2] = {(n_local + 1) / 2, n_local / 2};
-
-    auto t_d = [&](int s) { return tmem + s * 256 + lane_base; };
-    auto stage_of = [&](int s) { return smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES; };
-    auto tile_of = [&](int s, int j) { return cta_in_body + (s + 2 * j) * ctas_per_body; };
-
-    auto phase_py = [&](int s, int j) {         // x[t] boxes -> A columns 32..63 (k = 64 + channel)
-      uint8_t* my_y = stage_of(s) + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
-      mbar_wait(&bars->y_full[s], j & 1);
-      tc_prep16<BF16, SPLIT, PK>(my_y, r, sub * 4, t_d(s) + 128 + 32 + cq * 8, t_d(s) + 192 + 32 + cq * 8);
-    };
-    auto phase_px = [&](int s, int j) {         // x[t-d] boxes -> A columns 0..31, then the operand is complete
-      uint8_t* my_x = stage_of(s) + half * TC_BOX_BYTES + r * 128;
-      mbar_wait(&bars->x_full[s], j & 1);
-      if (tracer) TC_TRACE(s, j, 1);
-      tc_prep16<BF16, SPLIT, PK>(my_x, r, sub * 4, t_d(s) + 128 + cq * 8, t_d(s) + 192 + cq * 8);
-      mbar_arrive(&bars->x_free[s]);             // (release: my reads of the x[t-d] boxes are done)
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->a_ready[s]);
-      if (tracer) TC_TRACE(s, j, 4);
-    };
-    auto phase_co = [&](int s, int j) {         // copy the tile's output out of the x[t] boxes (full 128-byte lines)
-      // a box row is written by the two warps (sub = 0, 1) of this (lane quarter, box): pair barrier, then each
-      // of the two copies 16 of the pair's 32 rows
-      named_bar_sync(1 + quarter * 2 + half, 64);
-      const int tile = tile_of(s, j);
-      const int n = tile / p.tiles_per_utt, t_first = (tile % p.tiles_per_utt) * TC_TM;
-      uint8_t* box = stage_of(s) + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES;
-      float* out_tile = p.x_out + (((size_t)body * p.N + n) * p.T + t_first) * TC_C + half * 32;
-      const int chunk = lane & 7;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = quarter * 32 + sub * 16 + i * 4 + (lane >> 3);
-        const float4 v = *box_chunk(box + row * 128, row, chunk);
-        if (t_first + row < p.T) *reinterpret_cast<float4*>(out_tile + (size_t)row * TC_C + chunk * 4) = v;
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&bars->y_free[s]);             // (release: my reads of the x[t] boxes and conditioning rows are done)
-      if (tracer) TC_TRACE(s, j, 8);
-    };
-    auto phase_e1 = [&](int s, int j) {         // z = tanh(f) * sigmoid(g) on my 16 channels
-      const int tile = tile_of(s, j);
-      const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TC_TM, t = t0 + r;
-      const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
-      const float4* cb;
-      if (p.cb_in_smem) {
-        const int f0 = (t0 + p.hop / 2) / p.hop;
-        cb = reinterpret_cast<const float4*>(smem + TC_SMEM_CB0 + s * TC_CB_BYTES) + (frame - f0) * 32 + cq * 4;
-      } else {
-        cb = reinterpret_cast<const float4*>((body ? p.cbias[1] : p.cbias[0]) + ((size_t)n * p.t_mel + frame) * 128) + cq * 4;
-      }
-      uint8_t* my_y = stage_of(s) + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
-      mbar_wait(&bars->d1_ready[s], j & 1);
-      tc_fence_after_sync();
-      if (p.cb_in_smem) mbar_wait(&bars->c_full[s], j & 1);
-      if (tracer) TC_TRACE(s, j, 5);
-      uint32_t fr[16], gr[16];
-      tmem_ld16(t_d(s) + cq * 16, fr);
-      tmem_ld16(t_d(s) + 64 + cq * 16, gr);
-      tmem_wait_ld();
-      float z[16];
-      tc_gate<BF16, PK, 16>(fr, gr, cb, cb + 16, sf, sg, z);
-      if (p.mode == 1) {                // last layer: z itself is the output (x[t] is dead)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, sub * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-      } else {
-        uint32_t hi[8], lo[8];
-        float v0[8], v1[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
-        split8x<BF16, SPLIT, PK>(v0, hi, lo);
-        split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
-        tmem_st8(t_d(s) + 128 + cq * 8, hi);
-        if (SPLIT) tmem_st8(t_d(s) + 192 + cq * 8, lo);
-        tmem_wait_st();
-        tc_fence_before_sync();
-        mbar_arrive(&bars->z_ready[s]);
-      }
-      if (tracer) TC_TRACE(s, j, 6);
-    };
-    auto phase_e2 = [&](int s, int j) {         // out = x[t] + D2 + b_dense, in place in my staged x[t] quarter row
-      uint8_t* my_y = stage_of(s) + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
-      mbar_wait(&bars->d2_ready[s], j & 1);
-      tc_fence_after_sync();
-      if (tracer) TC_TRACE(s, j, 7);
-      uint32_t dr[16];
-      tmem_ld16(t_d(s) + cq * 16, dr);
-      tmem_wait_ld();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(bd_s + q * 4);
-        const float4 xv = *box_chunk(my_y, r, sub * 4 + q);
-        const uint32_t* d = &dr[q * 4];
-        float4 o;
-        if (PK) {
-          const uint64_t S2 = pk2(s2, s2);
-          upk2(add2(pk2(xv.x, xv.y), fma2(pk2(__uint_as_float(d[0]), __uint_as_float(d[1])), S2, pk2(b.x, b.y))), o.x, o.y);
-          upk2(add2(pk2(xv.z, xv.w), fma2(pk2(__uint_as_float(d[2]), __uint_as_float(d[3])), S2, pk2(b.z, b.w))), o.z, o.w);
-        } else {
-          o.x = xv.x + fmaf(__uint_as_float(d[0]), s2, b.x);
-          o.y = xv.y + fmaf(__uint_as_float(d[1]), s2, b.y);
-          o.z = xv.z + fmaf(__uint_as_float(d[2]), s2, b.z);
-          o.w = xv.w + fmaf(__uint_as_float(d[3]), s2, b.w);
-        }
-        *box_chunk(my_y, r, sub * 4 + q) = o;
-      }
-    };
-
-    if (n_local > 0) {
-      if (tracer) TC_TRACE(0, 0, 0);
-#pragma unroll 1
-      for (int s = 0; s < 2; ++s)
-        if (n_slot[s] > 0) phase_py(s, 0);
-      mbar_wait(&bars->w_ready, 0);     // scalars / bias live in the weight image
-      sf = scal[0]; sg = scal[1]; s2 = scal[2];
-#pragma unroll 1
-      for (int j = 0; j < n_slot[0]; ++j) {
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s)
-          if (j < n_slot[s]) phase_px(s, j);
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s)
-          if (j < n_slot[s]) {
-            phase_e1(s, j);
-            if (p.mode == 1) phase_co(s, j);
-          }
-        if (p.mode != 1) {
-#pragma unroll 1
-          for (int s = 0; s < 2; ++s)
-            if (j < n_slot[s]) {
-              phase_e2(s, j);
-              phase_co(s, j);
-            }
-        }
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s)
-          if (j + 1 < n_slot[s]) phase_py(s, j + 1);
-      }
-    }
   } else {
     // ======================= workers: operand prep, epilogues =======================
     // warp -> (tile slot, channel half, lane quarter); thread -> (row of the tile, 32 of the 64 channels)
@@ -958,288 +831,6 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
   tc_fence_before_sync();
   __syncthreads();
   if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_layer_tc3: the same layer, tile slots, TMEM layout, staging and barrier protocol as k_layer_tc, with
-// 1024 threads: 16 worker warps PER tile slot (a thread = one row x 16 channels) and no dedicated MMA /
-// TMA warps -- the first warp of each slot (its "chief") issues the slot's GEMMs and TMA refills at the
-// points of the tile's chain where it would otherwise wait for them.
-// Why (measured, profiles/r1_tc_trace_v14*.txt): with 8 warps per slot every worker phase is bound by the
-// dependent-issue latency of 2 warps per scheduler (operand prep 1.0k cycles for ~250 instructions per
-// thread, residual + copy-out 1.8k for ~160), not by any pipe; a slot's chain is 9k cycles of which 2.6k
-// are tensor work. 16 warps per slot run the same phases in 0.3k / 1.3k; the gate phase stays at the
-// MUFU floor (1.3k for 128 rows x 64 channels x 2.5 MUFU).  64 registers per thread (1024 threads).
-// ------------------------------------------------------------------------------------------------
-constexpr int TC3_THREADS = 1024;
-
-template <bool BF16, bool SPLIT>
-__global__ void __launch_bounds__(TC3_THREADS, 1)
-k_layer_tc3(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
-  using namespace ptx;
-  constexpr bool PK = true;
-  extern __shared__ __align__(1024) uint8_t tc_smem[];
-  uint8_t* smem = tc_smem;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem + TC_SMEM_BARS);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int body = blockIdx.x & 1;
-  const int cta_in_body = blockIdx.x >> 1, ctas_per_body = (gridDim.x + 1 - body) >> 1;
-  const int tiles_body = p.N * p.tiles_per_utt;
-  const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
-
-  pdl_launch_dependents();
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_init(&bars->w_ready, 1);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&bars->x_full[s], 1);
-        mbar_init(&bars->y_full[s], 1);
-        mbar_init(&bars->c_full[s], 1);
-        mbar_init(&bars->x_free[s], 512);
-        mbar_init(&bars->y_free[s], 512);
-        mbar_init(&bars->a_ready[s], 512);
-        mbar_init(&bars->d1_ready[s], 1);
-        mbar_init(&bars->z_ready[s], 512);
-        mbar_init(&bars->d2_ready[s], 1);
-      }
-      bars->mma_lock = 0;
-      fence_mbar_init();
-      const uint8_t* img = body ? p.image[1] : p.image[0];
-      mbar_arrive_expect_tx(&bars->w_ready, TC_IMAGE_BYTES);
-      for (int off = 0; off < TC_IMAGE_BYTES; off += 16384) {
-        const int n = min(16384, TC_IMAGE_BYTES - off);
-        bulk_g2s(smem + off, img + off, n, &bars->w_ready);
-      }
-    }
-    __syncwarp();
-    tmem_alloc(&bars->tmem_base, 512);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = bars->tmem_base;
-
-  // warp -> (tile slot, channel quarter, lane quarter); thread -> (row of the tile, 16 of the 64 channels)
-  const int slot = warp >> 4, cq = (warp >> 2) & 3, quarter = warp & 3, half = cq >> 1, sub = cq & 1;
-  const bool chief = (warp & 15) == 0;          // issues the slot's MMAs and TMA loads (lane 0)
-  const int r = quarter * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-  const uint32_t tD = tmem + slot * 256 + lane_base;
-  const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-  uint8_t* stage = smem + TC_SMEM_STAGE0 + slot * TC_STAGE_BYTES;
-  uint8_t* my_x = stage + half * TC_BOX_BYTES + r * 128;                       // x[t-d], my box row (chunks 4*sub ..)
-  uint8_t* my_y = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;    // x[t]; later the output
-  const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + cq * 16;
-  const float* scal = reinterpret_cast<const float*>(smem + TC_OFF_SCAL);
-  const float* cbias = body ? p.cbias[1] : p.cbias[0];
-  const int tiles_s = (n_local + 1 - slot) / 2;
-  const bool tracer = chief && lane == 0;
-
-  // ---- chief-only helpers (TMA loads of the slot's boxes / conditioning rows, the slot's GEMMs)
-  auto coords = [&](int j, int& n, int& t0) {
-    const int tile = cta_in_body + (slot + 2 * j) * ctas_per_body;
-    n = tile / p.tiles_per_utt;
-    t0 = (tile % p.tiles_per_utt) * TC_TM;
-  };
-  auto issue_x = [&](int j) {
-    int n, t0;
-    coords(j, n, t0);
-    mbar_arrive_expect_tx(&bars->x_full[slot], 2 * TC_BOX_BYTES);
-    tma_load_3d(stage, &map_in, 0, t0 - p.dilation, body * p.N + n, &bars->x_full[slot]);
-    tma_load_3d(stage + TC_BOX_BYTES, &map_in, 32, t0 - p.dilation, body * p.N + n, &bars->x_full[slot]);
-  };
-  auto issue_y = [&](int j) {     // x[t] boxes + the conditioning rows of the frames the tile touches
-    int n, t0;
-    coords(j, n, t0);
-    mbar_arrive_expect_tx(&bars->y_full[slot], 2 * TC_BOX_BYTES);
-    tma_load_3d(stage + 2 * TC_BOX_BYTES, &map_in, 0, t0, body * p.N + n, &bars->y_full[slot]);
-    tma_load_3d(stage + 3 * TC_BOX_BYTES, &map_in, 32, t0, body * p.N + n, &bars->y_full[slot]);
-    if (p.cb_in_smem) {
-      const int f0 = (t0 + p.hop / 2) / p.hop, f1 = (min(t0 + TC_TM - 1, p.T - 1) + p.hop / 2) / p.hop;
-      const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * 512;
-      mbar_arrive_expect_tx(&bars->c_full[slot], bytes);
-      bulk_g2s(smem + TC_SMEM_CB0 + slot * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[slot]);
-    }
-  };
-  const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
-  const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
-  constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
-  const uint32_t mD = tmem + slot * 256, mAhi = mD + 128, mAlo = mD + 192;     // (lane 0 addresses for the MMAs)
-
-  if (chief) {
-    if (lane == 0 && tiles_s > 0) {
-      tma_prefetch_desc(&map_in);
-      pdl_wait_prior_grid();      // the previous layer's output (and everything before it) is complete
-      // slot 1 lets slot 0's first boxes land first (the two tiles then start half a phase apart)
-      if (slot == 1) mbar_wait(&bars->y_full[0], 0);
-      issue_x(0);
-      issue_y(0);
-    }
-    __syncwarp();
-  }
-
-  float sf = 0.f, sg = 0.f, s2 = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < tiles_s; ++j) {
-    int n, t0;
-    coords(j, n, t0);
-    const uint32_t par = j & 1;
-
-    // ---- operand prep: A1 = [x[t-d] | x[t]] -> fp16 hi/lo -> TMEM (k = channel, +64 for the t tap)
-    if (tracer) TC_TRACE(slot, j, 0);
-    mbar_wait(&bars->x_full[slot], par);
-    if (tracer) TC_TRACE(slot, j, 1);
-    tc_prep16<BF16, SPLIT, PK>(my_x, r, sub * 4, tAhi + cq * 8, tAlo + cq * 8);
-    mbar_arrive(&bars->x_free[slot]);
-    if (tracer) TC_TRACE(slot, j, 2);
-    mbar_wait(&bars->y_full[slot], par);
-    if (tracer) TC_TRACE(slot, j, 3);
-    tc_prep16<BF16, SPLIT, PK>(my_y, r, sub * 4, tAhi + 32 + cq * 8, tAlo + 32 + cq * 8);
-    tmem_wait_st();
-    tc_fence_before_sync();
-    mbar_arrive(&bars->a_ready[slot]);
-    if (tracer) TC_TRACE(slot, j, 4);
-
-    if (chief) {
-      if (lane == 0) {
-        mbar_wait(&bars->a_ready[slot], par);       // every thread of the slot: operand written, boxes read
-        mbar_wait(&bars->x_free[slot], par);
-        if (j + 1 < tiles_s) issue_x(j + 1);       // x[t-d] boxes of the slot's next tile
-        if (j == 0) mbar_wait(&bars->w_ready, 0);
-        tc_lock<SPLIT>(&bars->mma_lock);
-        tc_fence_after_sync();
-        TC_TRACE(2, j, slot * 8 + 0);
-        uint32_t acc = 0;
-        if (SPLIT) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks, acc = 1)
-            mma_f16_ts(mD, mAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            mma_f16_ts(mD, mAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
-        }
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks, acc = 1)
-          mma_f16_ts(mD, mAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-        mma_commit(&bars->d1_ready[slot]);
-        tc_unlock<SPLIT>(&bars->mma_lock);
-        TC_TRACE(2, j, slot * 8 + 1);
-      }
-      __syncwarp();
-    }
-
-    if (j == 0) {                     // scalars / bias live in the weight image
-      mbar_wait(&bars->w_ready, 0);
-      sf = scal[0]; sg = scal[1]; s2 = scal[2];
-    }
-    const int frame = (min(t0 + r, p.T - 1) + p.hop / 2) / p.hop;
-    const float4* cb;
-    if (p.cb_in_smem) {
-      const int f0 = (t0 + p.hop / 2) / p.hop;
-      cb = reinterpret_cast<const float4*>(smem + TC_SMEM_CB0 + slot * TC_CB_BYTES) + (frame - f0) * 32 + cq * 4;
-    } else {
-      cb = reinterpret_cast<const float4*>(cbias + ((size_t)n * p.t_mel + frame) * 128) + cq * 4;
-    }
-
-    // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 16 channels, 8 per TMEM round trip (64 registers)
-    mbar_wait(&bars->d1_ready[slot], par);
-    tc_fence_after_sync();
-    if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
-    if (tracer) TC_TRACE(slot, j, 5);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t fr[8], gr[8];
-      tmem_ld8(tD + cq * 16 + c * 8, fr);
-      tmem_ld8(tD + 64 + cq * 16 + c * 8, gr);
-      tmem_wait_ld();
-      float z[8];
-      tc_gate<BF16, PK, 8>(fr, gr, cb + c * 2, cb + 16 + c * 2, sf, sg, z);
-      if (p.mode == 1) {                // last layer: z itself is the output (x[t] is dead)
-        *box_chunk(my_y, r, sub * 4 + c * 2) = make_float4(z[0], z[1], z[2], z[3]);
-        *box_chunk(my_y, r, sub * 4 + c * 2 + 1) = make_float4(z[4], z[5], z[6], z[7]);
-      } else {
-        uint32_t hi[4], lo[4];
-        split8x<BF16, SPLIT, PK>(z, hi, lo);
-        tmem_st4(tAhi + cq * 8 + c * 4, hi);
-        if (SPLIT) tmem_st4(tAlo + cq * 8 + c * 4, lo);
-      }
-    }
-    if (p.mode != 1) {
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->z_ready[slot]);
-      if (tracer) TC_TRACE(slot, j, 6);
-      if (chief) {
-        if (lane == 0) {
-          mbar_wait(&bars->z_ready[slot], par);
-          tc_lock<SPLIT>(&bars->mma_lock);
-          tc_fence_after_sync();
-          TC_TRACE(2, j, slot * 8 + 2);
-          uint32_t acc = 0;
-          if (SPLIT) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks, acc = 1)
-              mma_f16_ts(mD, mAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_f16_ts(mD, mAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks, acc = 1)
-            mma_f16_ts(mD, mAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-          mma_commit(&bars->d2_ready[slot]);
-          tc_unlock<SPLIT>(&bars->mma_lock);
-          TC_TRACE(2, j, slot * 8 + 3);
-        }
-        __syncwarp();
-      }
-
-      // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] quarter row)
-      mbar_wait(&bars->d2_ready[slot], par);
-      tc_fence_after_sync();
-      if (tracer) TC_TRACE(slot, j, 7);
-      uint32_t dr[16];
-      tmem_ld16(tD + cq * 16, dr);
-      tmem_wait_ld();
-      const uint64_t S2 = pk2(s2, s2);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(bd_s + q * 4);
-        const float4 xv = *box_chunk(my_y, r, sub * 4 + q);
-        const uint32_t* d = &dr[q * 4];
-        float4 o;
-        upk2(add2(pk2(xv.x, xv.y), fma2(pk2(__uint_as_float(d[0]), __uint_as_float(d[1])), S2, pk2(b.x, b.y))), o.x, o.y);
-        upk2(add2(pk2(xv.z, xv.w), fma2(pk2(__uint_as_float(d[2]), __uint_as_float(d[3])), S2, pk2(b.z, b.w))), o.z, o.w);
-        *box_chunk(my_y, r, sub * 4 + q) = o;
-      }
-    }
-    // ---- copy-out: the 4 warps of this (slot, lane quarter) wrote rows 32*quarter .. +31 of both x[t] boxes;
-    //      after a 128-thread barrier each copies 8 of those rows, a warp instruction = 2 full 256-byte rows
-    named_bar_sync(1 + slot * 4 + quarter, 128);
-    {
-      float* out_tile = p.x_out + (((size_t)body * p.N + n) * p.T + t0) * TC_C;
-      const int bx = (lane >> 3) & 1, chunk = lane & 7;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = quarter * 32 + cq * 8 + i * 2 + (lane >> 4);
-        const float4 v = *box_chunk(stage + (2 + bx) * TC_BOX_BYTES + row * 128, row, chunk);
-        if (t0 + row < p.T) *reinterpret_cast<float4*>(out_tile + (size_t)row * TC_C + bx * 32 + chunk * 4) = v;
-      }
-    }
-    tc_fence_before_sync();
-    mbar_arrive(&bars->y_free[slot]);          // (release: my reads of the x[t] boxes and conditioning rows are done)
-    if (tracer) TC_TRACE(slot, j, 8);
-    if (chief) {
-      if (lane == 0 && j + 1 < tiles_s) {
-        mbar_wait(&bars->y_free[slot], par);
-        issue_y(j + 1);
-      }
-      __syncwarp();
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
