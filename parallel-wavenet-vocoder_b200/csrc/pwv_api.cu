@@ -102,6 +102,8 @@ struct pwv_model {
   long long* trace = nullptr;    // pwv_debug_set_trace
   bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
   bool use_flags = true;         // tile handshake between consecutive gated layers (PWV_NO_TILE_FLAGS=1: off)
+  int tc_stagger = 0;            // PWV_TC_STAGGER (A/B runs): how far slot 1 starts behind slot 0 in k_flow_tc
+  bool use_flow = true;          // one persistent launch per flow (k_flow_tc); PWV_TC_FLOW=0: one launch per layer
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
@@ -196,6 +198,8 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -258,6 +262,8 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->max_layers = mx;
   m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
   m->use_flags = getenv("PWV_NO_TILE_FLAGS") == nullptr && m->use_pdl;
+  if (const char* v = getenv("PWV_TC_FLOW")) m->use_flow = atoi(v) != 0;
+  if (const char* v = getenv("PWV_TC_STAGGER")) m->tc_stagger = atoi(v);
   if (const char* v = getenv("PWV_TC_VARIANT")) {
     const int k = atoi(v);
     if (k >= 0 && k <= 1) m->tc_variant = k;
@@ -650,7 +656,41 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   size_t layer_base = 0;   // index of (flow, body 0, layer 0) in the image array
   for (int i = 0; i < flow; ++i) layer_base += 2 * (size_t)hp.n_layers[i];
   int cur = *cur_buf;
-  for (int j = 0; j < L; ++j) {
+  // One persistent launch for all gated layers of the flow (k_flow_tc). The per-layer launches below remain for
+  // per-launch profiling (mode 1), the layer tap of the parity tests, the phase trace and A/B runs (PWV_TC_FLOW=0).
+  const bool tap_layer = taps && taps->layer_out && taps->layer_flow == flow;
+  const bool flow_kernel = m->use_flow && m->use_flags && m->tc_variant == 0 && m->profiling != 1 && !tap_layer && (!m->trace || getenv("PWV_TRACE_FLOW")) &&
+                           L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms;
+  if (flow_kernel) {
+    pwv::TcFlowParams q;
+    q.act[0] = w.act[0]; q.act[1] = w.act[1];
+    q.images = m->tc.d_images + layer_base * pwv::TC_IMAGE_BYTES;
+    q.cbias = w.cbias;
+    q.flags = w.flags + (layer_base / 2) * 2 * (size_t)tiles_body;
+    q.N = N; q.T = T; q.t_mel = t_mel; q.hop = hp.hop_length; q.L = L; q.cur0 = cur; q.tiles_per_utt = tiles_per_utt;
+    q.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+    for (int j = 0; j < L; ++j) q.dilation[j] = hp.dilations[flow][j];
+    q.stagger = m->tc_stagger;
+    q.trace = m->trace; q.trace_layer = m->trace ? m->trace_launch - (int)(layer_base / 2) : -1;
+    if (m->profiling == 2) PWV_PROF_MARK(m, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(pwv::TCF_THREADS);
+    cfg.dynamicSmemBytes = pwv::TCF_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = m->use_pdl ? 1 : 0;
+    if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false>, maps[0], maps[1], q));
+    else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true>, maps[0], maps[1], q));
+    if (m->profiling == 2) PWV_PROF_MARK(m, st);
+    if (m->profiling) m->prof_launches += L;
+    ++*launches;
+    cur ^= (L & 1);
+  }
+  for (int j = 0; j < L && !flow_kernel; ++j) {
     pwv::TcLayerParams p;
     p.x_out = w.act[cur ^ 1];
     for (int b = 0; b < 2; ++b) {

@@ -834,6 +834,429 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_flow_tc: ALL gated layers of one flow (both bodies) in one persistent launch.
+//
+// Same tile pipeline as k_layer_tc (tile slots, TMEM layout, staging, warp roles, arithmetic -- the
+// results are bit-identical), with the layer loop inside the kernel and NO grid-wide synchronisation
+// between layers: a tile of layer l+1 starts as soon as the few tiles of layer l it depends on have been
+// published (per-tile flags, see k_layer_tc's tile handshake), whichever CTAs produced them. Measured
+// reason (c2, profiles/r1_tc_trace_v14_layer2.txt): of the 83k cycles a layer takes as a kernel of its own
+// only 63k are the steady-state pipeline; the rest is CTA exit -> launch -> prologue (barriers, TMEM,
+// 80 KB of weights) -> first loads, and the half-phase stagger of the two slots at both ends.
+// Here a CTA keeps walking its tile list layer after layer and the stagger survives the layer change.
+//
+// Weights are single-buffered (80 KB; two layers do not fit next to 128 KB of staging). They are
+// replaced in two parts by slot 0's MMA issuer: W1 (64 KB) + the bias/scale tail as soon as BOTH slots'
+// last GEMM1 of the layer has completed (tcgen05.commit on w1_free), W2 (16 KB) after both slots' last
+// GEMM2 -- by the time a slot's first tile of the next layer has been converted (1k cycles) W1 is
+// there. The 512-byte tail (dense bias, epilogue scales) is double-buffered by layer parity because the
+// workers still read it in the last tiles' residual step.
+//
+// Deadlock freedom: grid <= #SMs with one CTA per SM, so all CTAs are resident; every wait points at an
+// earlier (layer, tile) of some CTA or at this CTA's own other roles, never forward.
+// ------------------------------------------------------------------------------------------------
+constexpr int TCF_THREADS = TC_THREADS;                    // (a 21st warp would cap the kernel at 80 registers: 672 -> 768 threads' worth)
+constexpr int TCF_MAIN_BYTES = TC_OFF_BD;                  // W1hi | W1lo | W2hi | W2lo
+constexpr int TCF_TAIL_BYTES = 512;                        // dense bias (256 B) + scales (256 B)
+constexpr int TCF_SMEM_TAIL0 = TC_SMEM_CB0 + 2 * TC_CB_BYTES;
+constexpr int TCF_SMEM_BARS = TCF_SMEM_TAIL0 + 2 * TCF_TAIL_BYTES;
+constexpr int TCF_SMEM_BYTES = TCF_SMEM_BARS + 512;
+constexpr int TCF_MAX_LAYERS = 64;
+
+struct TcFlowParams {
+  float* act[2];            // ping/pong [2][N][T][64]; layer l reads act[(cur0 + l) & 1] through map[(cur0 + l) & 1], writes the other
+  const uint8_t* images;    // image of (flow, body 0, layer 0); (body b, layer l) at + (b * L + l) * TC_IMAGE_BYTES
+  const float* cbias;       // [2][L][N][t_mel][128] (pre-scaled, as for k_layer_tc)
+  int* flags;               // [L][2][N * tiles_per_utt], zeroed before the launch
+  int N, T, t_mel, hop, L, cur0, tiles_per_utt, cb_in_smem;
+  int dilation[TCF_MAX_LAYERS];
+  long long* trace;         // debug timeline of CTA 0 for layer trace_layer (or nullptr)
+  int trace_layer;
+  int stagger;              // see the producers
+};
+
+struct TcFlowBarriers {
+  uint64_t w1_ready, w2_ready, w1_free, w2_free;
+  uint64_t x_full[2], y_full[2], c_full[2], x_free[2], y_free[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
+  uint32_t tmem_base;
+  int mma_lock;
+};
+
+#define TCF_TRACE(role, l, j, k)                                                                    \
+  do {                                                                                              \
+    if (p.trace && blockIdx.x == 0 && (l) == p.trace_layer && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
+  } while (0)
+
+template <bool BF16, bool SPLIT, bool PK = false>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
+k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const __grid_constant__ TcFlowParams p) {
+  using namespace ptx;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* smem = tc_smem;
+  TcFlowBarriers* bars = reinterpret_cast<TcFlowBarriers*>(smem + TCF_SMEM_BARS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int body = blockIdx.x & 1;
+  const int cta_in_body = blockIdx.x >> 1, ctas_per_body = (gridDim.x + 1 - body) >> 1;
+  const int tiles_body = p.N * p.tiles_per_utt;
+  const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
+  const int L = p.L;
+
+  pdl_launch_dependents();
+  if (warp == TC_MMA_WARP) {
+    if (lane == 0) {
+      mbar_init(&bars->w1_ready, 1);
+      mbar_init(&bars->w2_ready, 1);
+      mbar_init(&bars->w1_free, 2);
+      mbar_init(&bars->w2_free, 2);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars->x_full[s], 1);
+        mbar_init(&bars->y_full[s], 1);
+        mbar_init(&bars->c_full[s], 1);
+        mbar_init(&bars->x_free[s], 256);
+        mbar_init(&bars->y_free[s], 256);
+        mbar_init(&bars->a_ready[s], 256);
+        mbar_init(&bars->d1_ready[s], 1);
+        mbar_init(&bars->z_ready[s], 256);
+        mbar_init(&bars->d2_ready[s], 1);
+      }
+      bars->mma_lock = 0;
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
+    // ======================= MMA issuers (one per tile slot); slot 0's also hands the weights over =======================
+    if (elect_one() && n_local > 0) {
+      const int s = warp - TC_MMA_WARP;
+      const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
+      const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
+      constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
+      const uint32_t tD = tmem + s * 256;
+      const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+      const int tiles_s = (n_local + 1 - s) / 2;
+      uint32_t it = 0;                                  // tiles of this slot so far (barrier phase)
+      for (int l = 0; l < L; ++l) {
+        const bool last_layer = l == L - 1;
+        const uint8_t* img = p.images + ((size_t)body * L + l) * TC_IMAGE_BYTES;
+        if (s == 0) {       // W1 + bias/scale tail of layer l, once BOTH slots' last GEMM1 of layer l-1 has completed
+          if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
+          mbar_arrive_expect_tx(&bars->w1_ready, 2 * TC_W1_BYTES + TCF_TAIL_BYTES);
+          for (int off = 0; off < 2 * TC_W1_BYTES; off += 16384) bulk_g2s(smem + off, img + off, 16384, &bars->w1_ready);
+          bulk_g2s(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES, img + TC_OFF_BD, TCF_TAIL_BYTES, &bars->w1_ready);
+        }
+        if (tiles_s == 0) {                             // (one tile in the CTA: slot 1 only keeps the weight hand-over going,
+          mbar_wait(&bars->w1_ready, l & 1);            //  in step with the layers: one arrival per barrier phase)
+          mbar_arrive(&bars->w1_free);
+          if (!last_layer) {
+            mbar_wait(&bars->w2_ready, l & 1);
+            mbar_arrive(&bars->w2_free);
+          }
+          continue;
+        }
+        for (int j = 0; j < tiles_s; ++j, ++it) {
+          mbar_wait(&bars->a_ready[s], it & 1);
+          if (j == 0) mbar_wait(&bars->w1_ready, l & 1);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TCF_TRACE(2, l, j, s * 8 + 0);
+          uint32_t acc = 0;
+          if (SPLIT) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks, acc = 1)
+              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks, acc = 1)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+          mma_commit(&bars->d1_ready[s]);
+          if (j == tiles_s - 1) mma_commit(&bars->w1_free);     // this slot is done with W1 of layer l
+          tc_unlock<SPLIT>(&bars->mma_lock);
+          TCF_TRACE(2, l, j, s * 8 + 1);
+          if (last_layer) continue;
+          if (s == 0 && j == 0) {     // W2 of layer l, once both slots' last GEMM2 of layer l-1 has completed
+            if (l > 0) mbar_wait(&bars->w2_free, (l - 1) & 1);
+            mbar_arrive_expect_tx(&bars->w2_ready, 2 * TC_W2_BYTES);
+            bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
+          }
+          mbar_wait(&bars->z_ready[s], it & 1);
+          if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TCF_TRACE(2, l, j, s * 8 + 2);
+          acc = 0;
+          if (SPLIT) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks, acc = 1)
+              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks, acc = 1)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+          mma_commit(&bars->d2_ready[s]);
+          if (j == tiles_s - 1) mma_commit(&bars->w2_free);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+          TCF_TRACE(2, l, j, s * 8 + 3);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= TC_TMA_WARP) {
+    // ======================= TMA producers (one per tile slot) =======================
+    if (elect_one()) {
+      const int s = warp - TC_TMA_WARP;
+      tma_prefetch_desc(&map0);
+      tma_prefetch_desc(&map1);
+      uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+      const int tiles_s = (n_local + 1 - s) / 2;
+      const int Q = L * tiles_s;                        // this slot's tile list: q = l * tiles_s + j
+      auto coords = [&](int j, int& n, int& t0) {
+        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+        n = tile / p.tiles_per_utt;
+        t0 = (tile % p.tiles_per_utt) * TC_TM;
+      };
+      auto map_of = [&](int l) { return ((p.cur0 + l) & 1) ? &map1 : &map0; };
+      auto issue_x = [&](int l, int j) {
+        int n, t0;
+        coords(j, n, t0);
+        const int d = p.dilation[l];
+        mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st, map_of(l), 0, t0 - d, body * p.N + n, &bars->x_full[s]);
+        tma_load_3d(st + TC_BOX_BYTES, map_of(l), 32, t0 - d, body * p.N + n, &bars->x_full[s]);
+      };
+      auto issue_y = [&](int l, int j) {     // x[t] boxes + the conditioning rows of the frames the tile touches
+        int n, t0;
+        coords(j, n, t0);
+        mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+        tma_load_3d(st + 2 * TC_BOX_BYTES, map_of(l), 0, t0, body * p.N + n, &bars->y_full[s]);
+        tma_load_3d(st + 3 * TC_BOX_BYTES, map_of(l), 32, t0, body * p.N + n, &bars->y_full[s]);
+        if (p.cb_in_smem) {
+          const float* cbias = p.cbias + ((size_t)body * L + l) * p.N * p.t_mel * 128;
+          const int f0 = (t0 + p.hop / 2) / p.hop, f1 = (min(t0 + TC_TM - 1, p.T - 1) + p.hop / 2) / p.hop;
+          const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * 512;
+          mbar_arrive_expect_tx(&bars->c_full[s], bytes);
+          bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
+        }
+      };
+      // the tiles of layer l-1 that tile j of layer l reads or whose reads it overwrites (see k_layer_tc): published?
+      auto tiles_ready = [&](int l, int j) -> bool {
+        if (l == 0) return true;
+        int n, t0;
+        coords(j, n, t0);
+        const int d = p.dilation[l], dp = p.dilation[l - 1];
+        const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
+        const int* f = p.flags + ((size_t)(l - 1) * 2 + body) * tiles_body + (size_t)n * p.tiles_per_utt;
+        const int hi = t0 + TC_TM - 1 - d, lo = max(t0 - d, 0);
+        const int k1 = hi >= 0 ? lo / TC_TM : k, k2 = hi >= 0 ? hi / TC_TM : k;
+        const int k3 = min(k + dp / TC_TM, last), k4 = min(k + (dp + TC_TM - 1) / TC_TM, last);
+        const int a = ld_relaxed_gpu(f + k), b = ld_relaxed_gpu(f + k1), c = ld_relaxed_gpu(f + k2);
+        const int d4 = ld_relaxed_gpu(f + k3), e = ld_relaxed_gpu(f + k4);
+        if (!(a & b & c & d4 & e)) return false;
+        fence_acq_rel_gpu();            // (acquire: the published tiles' rows are visible ...)
+        fence_proxy_async_global();     // (... to the TMA loads issued next)
+        return true;
+      };
+      auto publish = [&](int l, int j) {   // after y_free[s]: all 256 workers of the slot have stored the tile's output
+        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+        fence_acq_rel_gpu();               // (release, cumulative over the workers' stores observed through y_free)
+        st_relaxed_gpu(p.flags + ((size_t)l * 2 + body) * tiles_body + tile, 1);
+      };
+      pdl_wait_prior_grid();      // the flow's input (k_front) and everything before it is complete
+      // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0), when
+      // its first GEMM1 has completed (1) or when its first gate phase is through (2)
+      if (s == 1 && n_local > 0) {
+        if (p.stagger == 1) mbar_wait(&bars->d1_ready[0], 0);
+        else if (p.stagger == 2) mbar_wait(&bars->z_ready[0], 0);
+        else mbar_wait(&bars->y_full[0], 0);
+      }
+      if (Q > 0) {
+        issue_x(0, 0);
+        issue_y(0, 0);
+      }
+      // A tile is published as soon as it is stored, NEVER after a wait for other CTAs' tiles (two CTAs whose next
+      // tiles need each other's current tiles would wait forever): the inputs of the slot's next tile are only
+      // PROBED early (to prefetch its x[t-d] boxes, the normal case inside a layer); if they are not all there yet
+      // the blocking wait comes after this tile's publication.
+      for (int q = 0; q < Q; ++q) {
+        const int l = q / tiles_s, j = q - l * tiles_s;
+        if (q + 1 == Q) break;                          // (last layer: nothing to publish, nothing to refill)
+        const int ln = (q + 1) / tiles_s, jn = (q + 1) - ln * tiles_s;
+        mbar_wait(&bars->x_free[s], q & 1);             // the slot's x[t-d] boxes have been converted
+        const bool early = tiles_ready(ln, jn);
+        if (early) {
+          issue_x(ln, jn);
+          TCF_TRACE(3, l, j, s * 8 + 0);
+        }
+        mbar_wait(&bars->y_free[s], q & 1);             // output copied out of the x[t] boxes, conditioning rows read
+        if (early) {
+          issue_y(ln, jn);
+          if (l < L - 1) publish(l, j);
+        } else {
+          if (l < L - 1) publish(l, j);
+          while (!tiles_ready(ln, jn)) {
+          }
+          issue_x(ln, jn);
+          issue_y(ln, jn);
+        }
+        TCF_TRACE(3, l, j, s * 8 + 2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= workers: operand prep, epilogues =======================
+    const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tD = tmem + slot * 256 + lane_base;
+    const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+    uint8_t* stage = smem + TC_SMEM_STAGE0 + slot * TC_STAGE_BYTES;
+    uint8_t* my_x = stage + half * TC_BOX_BYTES + r * 128;
+    uint8_t* my_y = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
+    const bool tracer = (warp & 7) == 0 && lane == 0;
+    const int tiles_s = (n_local + 1 - slot) / 2;
+    uint32_t it = 0;
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      const bool last_layer = l == L - 1;
+      const float* tail = reinterpret_cast<const float*>(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES);
+      const float* bd_s = tail + half * 32;
+      const float* cbias_l = p.cbias + ((size_t)body * L + l) * p.N * p.t_mel * 128;
+      float* x_out = p.act[(p.cur0 + l + 1) & 1];
+      float sf = 0.f, sg = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < tiles_s; ++j, ++it) {
+        const int tile = cta_in_body + (slot + 2 * j) * ctas_per_body;
+        const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
+        const uint32_t par = it & 1;
+
+        if (tracer) TCF_TRACE(slot, l, j, 0);
+        mbar_wait(&bars->x_full[slot], par);
+        if (tracer) TCF_TRACE(slot, l, j, 1);
+        tc_prep<BF16, SPLIT, PK>(my_x, r, tAhi + half * 16, tAlo + half * 16);
+        mbar_arrive(&bars->x_free[slot]);
+        if (tracer) TCF_TRACE(slot, l, j, 2);
+        mbar_wait(&bars->y_full[slot], par);
+        if (tracer) TCF_TRACE(slot, l, j, 3);
+        tc_prep<BF16, SPLIT, PK>(my_y, r, tAhi + 32 + half * 16, tAlo + 32 + half * 16);
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[slot]);
+        if (tracer) TCF_TRACE(slot, l, j, 4);
+
+        if (j == 0) {                     // the layer's scales / dense bias arrive with W1
+          mbar_wait(&bars->w1_ready, l & 1);
+          sf = tail[64]; sg = tail[65]; s2 = tail[66];
+        }
+        const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
+        const float4* cb;
+        if (p.cb_in_smem) {
+          const int f0 = ((tile % p.tiles_per_utt) * TC_TM + p.hop / 2) / p.hop;
+          cb = reinterpret_cast<const float4*>(smem + TC_SMEM_CB0 + slot * TC_CB_BYTES) + (frame - f0) * 32 + half * 8;
+        } else {
+          cb = reinterpret_cast<const float4*>(cbias_l + ((size_t)n * p.t_mel + frame) * 128) + half * 8;
+        }
+
+        // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
+        mbar_wait(&bars->d1_ready[slot], par);
+        tc_fence_after_sync();
+        if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
+        if (tracer) TCF_TRACE(slot, l, j, 5);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t fr[16], gr[16];
+          tmem_ld16(tD + half * 32 + c * 16, fr);
+          tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
+          tmem_wait_ld();
+          if (tracer) TCF_TRACE(slot, l, j, 12 + c);
+          float z[16];
+          tc_gate<BF16, PK, 16>(fr, gr, cb + c * 4, cb + 16 + c * 4, sf, sg, z);
+          if (last_layer) {               // z itself is the output (x[t] is dead)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+          } else {
+            uint32_t hi[8], lo[8];
+            float v0[8], v1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
+            split8x<BF16, SPLIT, PK>(v0, hi, lo);
+            split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
+            tmem_st8(tAhi + half * 16 + c * 8, hi);
+            if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+          }
+        }
+        if (!last_layer) {
+          tmem_wait_st();
+          tc_fence_before_sync();
+          mbar_arrive(&bars->z_ready[slot]);
+          if (tracer) TCF_TRACE(slot, l, j, 6);
+
+          // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] half row)
+          mbar_wait(&bars->d2_ready[slot], par);
+          tc_fence_after_sync();
+          if (tracer) TCF_TRACE(slot, l, j, 7);
+          uint32_t dr[2][16];
+          tmem_ld16(tD + half * 32, dr[0]);
+          tmem_ld16(tD + half * 32 + 16, dr[1]);
+          tmem_wait_ld();
+          if (tracer) TCF_TRACE(slot, l, j, 9);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(bd_s + q * 4);
+            const float4 xv = *box_chunk(my_y, r, q);
+            const uint32_t* d = &dr[q >> 2][(q & 3) * 4];
+            float4 o;
+            if (PK) {
+              const uint64_t S2 = pk2(s2, s2);
+              upk2(add2(pk2(xv.x, xv.y), fma2(pk2(__uint_as_float(d[0]), __uint_as_float(d[1])), S2, pk2(b.x, b.y))), o.x, o.y);
+              upk2(add2(pk2(xv.z, xv.w), fma2(pk2(__uint_as_float(d[2]), __uint_as_float(d[3])), S2, pk2(b.z, b.w))), o.z, o.w);
+            } else {
+              o.x = xv.x + fmaf(__uint_as_float(d[0]), s2, b.x);
+              o.y = xv.y + fmaf(__uint_as_float(d[1]), s2, b.y);
+              o.z = xv.z + fmaf(__uint_as_float(d[2]), s2, b.z);
+              o.w = xv.w + fmaf(__uint_as_float(d[3]), s2, b.w);
+            }
+            *box_chunk(my_y, r, q) = o;
+          }
+        }
+        // ---- copy-out (see k_layer_tc)
+        if (tracer) TCF_TRACE(slot, l, j, 10);
+        __syncwarp();
+        {
+          uint8_t* box = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES;
+          const int t_first = (tile % p.tiles_per_utt) * TC_TM;
+          float* out_tile = x_out + (((size_t)body * p.N + n) * p.T + t_first) * TC_C + half * 32;
+          const int chunk = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = quarter * 32 + i * 4 + (lane >> 3);
+            const float4 v = *box_chunk(box + row * 128, row, chunk);
+            if (t_first + row < p.T) *reinterpret_cast<float4*>(out_tile + (size_t)row * TC_C + chunk * 4) = v;
+          }
+        }
+        if (tracer) TCF_TRACE(slot, l, j, 11);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->y_free[slot]);
+        if (tracer) TCF_TRACE(slot, l, j, 8);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Post-net of both bodies on the tensor cores (reference modules.py:145-165, use_skip_connection
 // False): per 128-row tile
 //   D [128 x 128] = z . Ws                     (the last layer's skip 1x1; z from k_layer_tc mode 1)

@@ -264,3 +264,34 @@ def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision
             ref = _oracle(hp, weights, noise, mel)
             assert np.abs(got.cpu().numpy() - ref).max() <= TOL
         del model
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
+def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision):
+    """k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
+    the same tile pipeline as the one-launch-per-layer path (PWV_TC_FLOW=0): outputs must be BIT-identical,
+    including one-tile CTAs (idle second slot), single-layer flows (no GEMM2 at all), d >= T and ragged tiles."""
+    W = pkg('weights')
+    cases = [(None, 2, 4000), (((1, 512, 2), (256, 1)), 5, 1040), (((1, 512, 2), (256, 1)), 1, 80), (((1,), (2, 4), (128,)), 3, 2000),
+             (((1, 2, 4, 8, 16, 32, 64, 128, 256, 512) * 3,), 4, 8000), (None, 8, 16000)]
+    for dil, n, t in cases:
+        if dil is None:
+            hp.set_hparam_yaml('default')
+            hp.engine.precision = precision
+        else:
+            small_case(hp, dilations=dil, n=n, t=t, precision=precision)
+        weights = W.init_weights(hp, seed=4, bias_std=0.1)
+        noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=31, noise_seed=32)
+        monkeypatch.setenv('PWV_TC_FLOW', '0')
+        base, _ = _run(hp, weights, noise, mel, precision=precision)
+        monkeypatch.setenv('PWV_TC_FLOW', '1')
+        got, model = _run(hp, weights, noise, mel, precision=precision)
+        for _ in range(3):      # the handshake is timing dependent: repeat
+            again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
+            assert torch.equal(got, again), (dil, n, t, 'not deterministic')
+        assert torch.equal(got, base), (dil, n, t, float((got - base).abs().max()))
+        if precision == 'f16x3' and n * t <= 8000:
+            ref = _oracle(hp, weights, noise, mel)
+            assert np.abs(got.cpu().numpy() - ref).max() <= TOL
+        del model

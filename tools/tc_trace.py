@@ -27,7 +27,7 @@ torch.cuda.synchronize()
 L.check(m.lib.pwv_debug_set_trace(m._h, None, -1))
 t = buf.cpu().numpy().reshape(4, 16, 16)
 base = t[t > 0].min()
-names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_ready']
+names = ['enter', 'x_landed', 'x_prepped', 'y_landed', 'a_ready', 'd1_ready', 'z_ready', 'd2_ready', 'out_ready', 'e2_loaded', 'e2_done', 'copied', 'e1_ld0', 'e1_ld1']
 print(f'precision {prec}, variant {os.environ.get("PWV_TC_VARIANT", "default")}, gated layer {launch}; cycles since the first stamp (delta from the previous event)')
 for role in (0, 1):
     print(f'--- worker slot {role}')
@@ -35,9 +35,9 @@ for role in (0, 1):
         row = t[role, j]
         if not row.any(): break
         s, prev = [], row[row > 0].min()
-        for k, nm in enumerate(names):
+        for k in sorted(range(len(names)), key=lambda k: row[k]):
             if row[k] == 0: continue
-            s.append(f'{nm}={row[k]-base}(+{row[k]-prev})')
+            s.append(f'{names[k]}={row[k]-base}(+{row[k]-prev})')
             prev = row[k]
         print(f' tile {j}: ' + ' '.join(s))
 print('--- MMA thread: [slot][phase] ready-seen / issued')
