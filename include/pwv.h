@@ -40,9 +40,14 @@
 extern "C" {
 #endif
 
-#define PWV_VERSION 100          /* major*10000 + minor*100 + patch */
+#define PWV_VERSION 101          /* major*10000 + minor*100 + patch */
 #define PWV_MAX_FLOWS 8
 #define PWV_MAX_LAYERS 64
+#define PWV_MAX_UPSAMPLE 4
+
+/* mel -> sample-rate conditioning (reference models.py:105-136) */
+#define PWV_UPSAMPLE_REPEAT 0            /* 1x1 conv + relu, every frame repeated hop times (default)       */
+#define PWV_UPSAMPLE_TRANSPOSED_CONV 1   /* stacked conv2d_transpose (kernel = stride) + relu per stage      */
 
 /* error codes */
 #define PWV_OK 0
@@ -76,6 +81,9 @@ typedef struct pwv_hparams {
   int32_t precision;              /* PWV_PREC_*                                                */
   int32_t n_layers[PWV_MAX_FLOWS];                     /* len(model.dilations[i])              */
   int32_t dilations[PWV_MAX_FLOWS][PWV_MAX_LAYERS];    /* model.dilations[i][j]                */
+  int32_t cond_upsample;          /* model.cond_upsample_method: PWV_UPSAMPLE_REPEAT | _TRANSPOSED_CONV  */
+  int32_t n_upsample;             /* transposed_conv: number of stages (reference models.py:23: 3) ...   */
+  int32_t upsample_strides[PWV_MAX_UPSAMPLE];  /* ... and their strides ([4,4,5]); product == hop_length  */
 } pwv_hparams;
 
 /* Optional debug taps for parity tests (all device pointers, any may be NULL). */
@@ -95,9 +103,9 @@ int pwv_device_count(void);
 int pwv_model_create(const pwv_hparams* hp, pwv_model** out);
 int pwv_model_destroy(pwv_model* m);
 
-/* Number of variables the model expects, and the i-th one's TF name / shape (ndim <= 3). */
+/* Number of variables the model expects, and the i-th one's TF name / shape (ndim <= 4). */
 int pwv_model_num_variables(const pwv_model* m);
-int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[3], int* ndim);
+int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[4], int* ndim);
 
 /* Copy one variable (HOST pointer, float32, TF layout) into the model's staging area. */
 int pwv_model_load_weight(pwv_model* m, const char* tf_name, const float* host_data,

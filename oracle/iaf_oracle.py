@@ -23,6 +23,7 @@ All functions take/return numpy arrays; `dtype` float64 is ground truth, float32
 import numpy as np
 
 ROOT = 'iaf_vocoder'
+UPSAMPLE_STRIDES = (4, 4, 5)     # the constant reference models.py:26 passes to _upsample_cond
 
 
 # ----------------------------------------------------------------------------- array backends
@@ -201,6 +202,23 @@ def upsample_cond_repeat(mel, w_dense, hop):
     return cond[:, hop // 2: -hop // 2, :]                                   # :133
 
 
+def upsample_cond_transposed(mel, W, strides, hop):
+    """Reference models.py:109-124 (normalize_cond ''): per stage i, tf.nn.conv2d_transpose of the (n, 1, len, Cin)
+    sequence with filter w_i [1, stride, Cout, Cin], strides [1, 1, stride, 1], SAME padding, then relu. The filter
+    is exactly as wide as the stride, so output position l*stride + j has the single source l:
+        out[n, l*stride + j, co] = sum_ci in[n, l, ci] * w_i[0, j, co, ci]
+    (conv2d_transpose is the gradient of conv2d w.r.t. its input: no kernel flip). Crop hop//2 at both ends."""
+    cond = mel
+    for i, stride in enumerate(strides):
+        w = W[f'{ROOT}/cond/transposed_conv_{i}_weights']                    # :113-115
+        n, length, cin = cond.shape
+        assert w.shape[0] == 1 and w.shape[1] == stride and w.shape[3] == cin, (w.shape, stride, cin)
+        cout = w.shape[2]
+        out = cond.reshape(n * length, cin) @ w[0].reshape(stride * cout, cin).T       # [n*len, stride*cout]
+        cond = _OPS.relu(out.reshape(n, length * stride, cout))                        # :118-120
+    return cond[:, hop // 2: -hop // 2, :]                                   # :124
+
+
 def logistic_noise(shape, seed, dtype=np.float64):
     """Sample of Logistic(0,1) as tf.contrib.distributions does it: log(u) - log1p(-u), u~U(0,1)
     (reference models.py:32-33). Deterministic stand-in with u clipped to [1e-7, 1-1e-7]."""
@@ -229,7 +247,10 @@ def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dty
     mel = _OPS.asarray(mel, dtype)
     x = _OPS.asarray(noise, dtype).reshape(noise.shape[0], noise.shape[1], 1)
     n, t, _ = x.shape
-    cond = upsample_cond_repeat(mel, W[f'{ROOT}/cond/dense'], hop)           # models.py:26
+    if f'{ROOT}/cond/dense' in W:
+        cond = upsample_cond_repeat(mel, W[f'{ROOT}/cond/dense'], hop)       # models.py:26,127-133
+    else:
+        cond = upsample_cond_transposed(mel, W, UPSAMPLE_STRIDES, hop)       # models.py:26,109-124
     if cond.shape[1] != t:
         raise ValueError(f'cond length {cond.shape[1]} != {t}: length must be a multiple of hop '
                          f'and mel must have 1 + length//hop frames')

@@ -151,7 +151,29 @@ def _relu(x, **_):
     return np.maximum(x, 0)
 
 
-nn = types.SimpleNamespace(conv1d=_conv1d, relu=_relu)
+def _conv2d_transpose(value, filter, output_shape, strides, padding='SAME', **_):   # noqa: A002 (mirrors tf)
+    """tf.nn.conv2d_transpose (NHWC; filter [height, width, out_channels, in_channels]) = the gradient of conv2d
+    with respect to its input: every input pixel scatters filter * pixel into the output at its strided
+    position (no kernel flip). Restated for what the reference calls (models.py:116-117): height 1, SAME
+    padding; with SAME, conv2d pads (k - s) in total when the output length is a multiple of the stride,
+    split floor/ceil, and the transpose drops those positions again."""
+    n, h, w_in, cin = value.shape
+    kh, kw, cout, cin2 = filter.shape
+    assert h == 1 and kh == 1 and cin == cin2 and padding == 'SAME' and list(strides[:2]) == [1, 1] and strides[3] == 1
+    s = int(strides[2])
+    out_w = int(output_shape[2])
+    assert tuple(int(v) for v in output_shape) == (n, 1, out_w, cout) and out_w == w_in * s
+    pad_total = max(kw - s, 0)
+    pad_left = pad_total // 2
+    full = np.zeros((n, 1, (w_in - 1) * s + kw, cout), dtype=np.result_type(value, filter))
+    for j in range(kw):
+        full[:, 0, j:j + (w_in - 1) * s + 1:s, :] += np.einsum('nlc,oc->nlo', value[:, 0], filter[0, j])
+    if full.shape[2] < out_w + pad_left:       # kernel narrower than the stride: untouched positions stay zero
+        full = np.pad(full, [(0, 0), (0, 0), (0, out_w + pad_left - full.shape[2]), (0, 0)])
+    return full[:, :, pad_left:pad_left + out_w, :]
+
+
+nn = types.SimpleNamespace(conv1d=_conv1d, relu=_relu, conv2d_transpose=_conv2d_transpose)
 
 
 class _EMA(object):

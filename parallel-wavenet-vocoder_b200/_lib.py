@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get('PWV_LIB') or os.path.join(_HERE, 'libpwv_b200.so')   
 
 PWV_MAX_FLOWS = 8
 PWV_MAX_LAYERS = 64
+PWV_MAX_UPSAMPLE = 4
+UPSAMPLE = {'repeat': 0, 'transposed_conv': 1}
 PREC = {'fp32': 0, 'f16x3': 1, 'bf16': 2}
 
 EXPORTS = (
@@ -32,6 +34,8 @@ class PwvHparams(ctypes.Structure):
         ('precision', ctypes.c_int32),
         ('n_layers', ctypes.c_int32 * PWV_MAX_FLOWS),
         ('dilations', (ctypes.c_int32 * PWV_MAX_LAYERS) * PWV_MAX_FLOWS),
+        ('cond_upsample', ctypes.c_int32), ('n_upsample', ctypes.c_int32),
+        ('upsample_strides', ctypes.c_int32 * PWV_MAX_UPSAMPLE),
     ]
 
 
@@ -110,6 +114,16 @@ def make_hparams(dims, precision='fp32'):
     h.use_biases = int(dims['use_biases'])
     h.use_skip_connection = int(dims['use_skip'])
     h.precision = PREC[precision]
+    method = dims.get('cond_upsample', 'repeat')
+    if method not in UPSAMPLE:
+        raise ValueError(f'model.cond_upsample_method must be one of {sorted(UPSAMPLE)}, got {method!r}')
+    h.cond_upsample = UPSAMPLE[method]
+    strides = list(dims.get('upsample_strides', ())) if method == 'transposed_conv' else []
+    if len(strides) > PWV_MAX_UPSAMPLE:
+        raise ValueError(f'{len(strides)} upsample stages > {PWV_MAX_UPSAMPLE}')
+    h.n_upsample = len(strides)
+    for i, st in enumerate(strides):
+        h.upsample_strides[i] = int(st)
     if dims['n_iaf'] > PWV_MAX_FLOWS:
         raise ValueError(f'n_iaf {dims["n_iaf"]} > {PWV_MAX_FLOWS}')
     for i, dil in enumerate(dims['dilations']):

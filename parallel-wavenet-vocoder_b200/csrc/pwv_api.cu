@@ -42,7 +42,7 @@ int fail(int code, const char* fmt, ...) {
 
 struct VarSpec {
   std::string name;
-  int64_t shape[3];
+  int64_t shape[4];
   int ndim;
   size_t numel() const {
     size_t n = 1;
@@ -81,6 +81,7 @@ struct pwv_model {
   int device = 0;
 
   size_t off_wc = 0;             // cond dense [n_mels][Cc]
+  size_t off_wup[PWV_MAX_UPSAMPLE] = {0, 0, 0, 0};   // transposed_conv stage i: [Cin][stride_i * Cc]
   std::vector<BodyOff> bodies;   // [flow*2 + body]
   float* d_arena = nullptr;
   size_t arena_floats = 0;
@@ -138,7 +139,7 @@ static void add_var(pwv_model* m, const std::string& name, std::initializer_list
   v.ndim = (int)shape.size();
   int i = 0;
   for (auto s : shape) v.shape[i++] = s;
-  for (; i < 3; ++i) v.shape[i] = 1;
+  for (; i < 4; ++i) v.shape[i] = 1;
   m->var_index[name] = (int)m->vars.size();
   m->vars.push_back(v);
 }
@@ -147,7 +148,16 @@ static void build_var_list(pwv_model* m) {
   const pwv_hparams& hp = m->hp;
   const int64_t k = hp.filter_width, R = hp.residual_channels, D = hp.dilation_channels,
                 S = hp.skip_channels, Cc = hp.condition_channels;
-  add_var(m, "iaf_vocoder/cond/dense", {1, hp.n_mels, Cc});
+  if (hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
+    // reference models.py:109-124: w_i [1, stride_i, Cc (out), Cin]; Cin = n_mels for stage 0, Cc afterwards
+    int64_t cin = hp.n_mels;
+    for (int i = 0; i < hp.n_upsample; ++i) {
+      add_var(m, "iaf_vocoder/cond/transposed_conv_" + std::to_string(i) + "_weights", {1, hp.upsample_strides[i], Cc, cin});
+      cin = Cc;
+    }
+  } else {
+    add_var(m, "iaf_vocoder/cond/dense", {1, hp.n_mels, Cc});
+  }
   for (int i = 0; i < hp.n_iaf; ++i)
     for (int b = 0; b < 2; ++b) {
       std::string p = "iaf_vocoder/iaf" + std::to_string(i) + "/" + kBodies[b];
@@ -240,6 +250,18 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
     return fail(PWV_EINVAL, "use_skip_connection=True is implemented on the fp32 path only (precision fp32), not on the tensor-core kernels");
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
+  if (hp->cond_upsample != PWV_UPSAMPLE_REPEAT && hp->cond_upsample != PWV_UPSAMPLE_TRANSPOSED_CONV)
+    return fail(PWV_EINVAL, "unknown cond_upsample %d", hp->cond_upsample);
+  if (hp->cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
+    if (hp->n_upsample < 1 || hp->n_upsample > PWV_MAX_UPSAMPLE) return fail(PWV_EINVAL, "n_upsample=%d out of range [1,%d]", hp->n_upsample, PWV_MAX_UPSAMPLE);
+    long long prod = 1;
+    for (int i = 0; i < hp->n_upsample; ++i) {
+      if (hp->upsample_strides[i] < 1) return fail(PWV_EINVAL, "upsample stride %d is %d", i, hp->upsample_strides[i]);
+      prod *= hp->upsample_strides[i];
+    }
+    if (prod != hp->hop_length)   // reference models.py:106
+      return fail(PWV_EINVAL, "product of the upsample strides (%lld) must equal hop_length (%d)", prod, hp->hop_length);
+  }
   if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_F16X3 && hp->precision != PWV_PREC_BF16)
     return fail(PWV_EINVAL, "unknown precision %d", hp->precision);
   if (hp->precision != PWV_PREC_FP32 && C != 64)
@@ -288,11 +310,11 @@ int pwv_model_num_variables(const pwv_model* m) {
   return (int)m->vars.size();
 }
 
-int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[3], int* ndim) {
+int pwv_model_variable(const pwv_model* m, int index, const char** name, int64_t shape[4], int* ndim) {
   if (!m || index < 0 || index >= (int)m->vars.size()) return fail(PWV_EINVAL, "bad model/index");
   const VarSpec& v = m->vars[index];
   if (name) *name = v.name.c_str();
-  if (shape) for (int i = 0; i < 3; ++i) shape[i] = v.shape[i];
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = v.shape[i];
   if (ndim) *ndim = v.ndim;
   return PWV_OK;
 }
@@ -327,8 +349,22 @@ int pwv_model_finalize(pwv_model* m) {
     arena.resize(off + n, 0.f);
     return off;
   };
-  m->off_wc = put((size_t)hp.n_mels * Cc);
-  {
+  if (hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
+    // stage i as a row GEMM: out[row][j*Cc + co] = relu(sum_ci in[row][ci] * w[0][j][co][ci]), i.e. B[ci][j*Cc + co];
+    // the output viewed as [rows * stride][Cc] is the upsampled sequence (kernel width == stride: no overlap)
+    int cin = hp.n_mels;
+    for (int i = 0; i < hp.n_upsample; ++i) {
+      const int sN = hp.upsample_strides[i];
+      m->off_wup[i] = put((size_t)cin * sN * Cc);
+      const auto& w = var(m, "iaf_vocoder/cond/transposed_conv_" + std::to_string(i) + "_weights");
+      for (int j = 0; j < sN; ++j)
+        for (int co = 0; co < Cc; ++co)
+          for (int ci = 0; ci < cin; ++ci)
+            arena[m->off_wup[i] + (size_t)ci * sN * Cc + (size_t)j * Cc + co] = w[((size_t)j * Cc + co) * cin + ci];
+      cin = Cc;
+    }
+  } else {
+    m->off_wc = put((size_t)hp.n_mels * Cc);
     const auto& w = var(m, "iaf_vocoder/cond/dense");
     std::copy(w.begin(), w.end(), arena.begin() + m->off_wc);
   }
@@ -471,8 +507,9 @@ int pwv_model_finalize(pwv_model* m) {
 // workspace carving (all blocks 256-byte aligned)
 // ------------------------------------------------------------------------------------------------
 struct Workspace {
-  float* cproj;     // [N][t_mel][Cc]
-  float* cbias;     // [2][Lmax][N][t_mel][2C]
+  float* cproj;     // [N][cond_rows][Cc]   cond_rows = t_mel ('repeat') or T ('transposed_conv')
+  float* cbias;     // [2][Lmax][N][cond_rows][2C]
+  float* up[2];     // transposed_conv: stage outputs (ping/pong)
   float* act[2];    // ping/pong, each [2][N][T][C]
   float* ss;        // [2][N][T] scale, shift
   float* x[2];      // [N][T] ping/pong
@@ -483,16 +520,35 @@ struct Workspace {
   size_t bytes;
 };
 
+// Conditioning rows per utterance and samples per row: 'repeat' keeps the per-layer conditioning terms at mel
+// rate (row = frame (s + hop/2) / hop); 'transposed_conv' produces a different vector for every sample.
+static int cond_rows(const pwv_model* m, int T) {
+  return m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV ? T : 1 + T / m->hp.hop_length;
+}
+static int cond_hop(const pwv_model* m) { return m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV ? 1 : m->hp.hop_length; }
+
 static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   const int C = m->C, t_mel = 1 + T / m->hp.hop_length;
+  const bool tconv = m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV;
+  const size_t crows = tconv ? (size_t)T : (size_t)t_mel;     // conditioning rows per utterance (cond_rows)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
     off += (bytes + 255) / 256 * 256;
     return p;
   };
-  w->cproj = (float*)take(sizeof(float) * (size_t)N * t_mel * m->Cc);
-  w->cbias = (float*)take(sizeof(float) * (size_t)2 * m->max_layers * N * t_mel * 2 * C);
+  w->cproj = (float*)take(sizeof(float) * (size_t)N * crows * m->Cc);
+  w->cbias = (float*)take(sizeof(float) * (size_t)2 * m->max_layers * N * crows * 2 * C);
+  w->up[0] = w->up[1] = nullptr;
+  if (tconv) {      // ping/pong stage outputs; the last stage has N * t_mel * hop rows
+    size_t rows = (size_t)N * t_mel, big[2] = {0, 0};
+    for (int i = 0; i < m->hp.n_upsample; ++i) {
+      rows *= m->hp.upsample_strides[i];
+      if (rows > big[i & 1]) big[i & 1] = rows;
+    }
+    w->up[0] = (float*)take(sizeof(float) * big[0] * m->Cc);
+    w->up[1] = (float*)take(sizeof(float) * (big[1] ? big[1] : 1) * m->Cc);
+  }
   w->act[0] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
   w->act[1] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
   w->ss = (float*)take(sizeof(float) * (size_t)2 * N * T);
@@ -552,7 +608,7 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
                               const pwv_taps* taps, int* cur_buf, int* launches) {
   using Cfg = pwv::TileCfg<C>;
   const pwv_hparams& hp = m->hp;
-  const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
+  const int L = hp.n_layers[flow], t_mel = cond_rows(m, T), c_hop = cond_hop(m);
   dim3 grid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
   int cur = *cur_buf;
   for (int j = 0; j < L; ++j) {
@@ -566,7 +622,7 @@ static int launch_layers_simt(pwv_model* m, const Workspace& w, int flow, int N,
       p.bd[b] = m->d_arena + lo.bd;
       p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
     }
-    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = c_hop; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : (hp.use_skip_connection ? 2 : 0);
     p.z_out = w.zbuf;
     PWV_PROF_MARK(m, st);
@@ -640,7 +696,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
                             const pwv_taps* taps, int* cur_buf, int* launches) {
   constexpr int C = pwv::TC_C;
   const pwv_hparams& hp = m->hp;
-  const int L = hp.n_layers[flow], t_mel = 1 + T / hp.hop_length;
+  const int L = hp.n_layers[flow], t_mel = cond_rows(m, T), c_hop = cond_hop(m);
   const bool bf16 = hp.precision == PWV_PREC_BF16;
   // layer-kernel variant (PWV_TC_VARIANT, read at pwv_model_create): 0 = scalar epilogue arithmetic,
   // 1 = packed fp32x2 epilogue arithmetic (bit-identical). Two more variants were measured and removed
@@ -667,8 +723,8 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     q.images = m->tc.d_images + layer_base * pwv::TC_IMAGE_BYTES;
     q.cbias = w.cbias;
     q.flags = w.flags + (layer_base / 2) * 2 * (size_t)tiles_body;
-    q.N = N; q.T = T; q.t_mel = t_mel; q.hop = hp.hop_length; q.L = L; q.cur0 = cur; q.tiles_per_utt = tiles_per_utt;
-    q.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+    q.N = N; q.T = T; q.t_mel = t_mel; q.hop = c_hop; q.L = L; q.cur0 = cur; q.tiles_per_utt = tiles_per_utt;
+    q.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
     for (int j = 0; j < L; ++j) q.dilation[j] = hp.dilations[flow][j];
     q.stagger = m->tc_stagger;
     q.trace = m->trace; q.trace_layer = m->trace ? m->trace_launch - (int)(layer_base / 2) : -1;
@@ -697,7 +753,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       p.image[b] = m->tc.d_images + (layer_base + (size_t)b * L + j) * pwv::TC_IMAGE_BYTES;
       p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
     }
-    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = hp.hop_length; p.dilation = hp.dilations[flow][j];
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = c_hop; p.dilation = hp.dilations[flow][j];
     p.mode = (j == L - 1) ? 1 : 0;
     p.tiles_per_utt = tiles_per_utt;
     {
@@ -708,7 +764,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       p.flags_in = (m->use_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
       p.prev_dilation = j > 0 ? hp.dilations[flow][j - 1] : 0;
     }
-    p.cb_in_smem = ((pwv::TC_TM - 1) / hp.hop_length + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+    p.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
     p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
     if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
     {
@@ -769,8 +825,30 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   PWV_PROF_MARK(m, st);   // [1] placeholder, re-recorded at the end
   if (w.flags) PWV_CUDA(cudaMemsetAsync(w.flags, 0, w.flags_bytes, st));
 
-  // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
-  {
+  const int crows = cond_rows(m, T);     // conditioning rows per utterance (t_mel, or T for transposed_conv)
+  if (hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
+    // reference models.py:109-124: stacked conv2d_transpose (kernel width = stride, so every output position has
+    // exactly one source frame) + relu per stage, then the crop [hop/2 : -hop/2]. Stage i is a row GEMM
+    // [rows][Cin] x [Cin][stride * Cc] whose output, read as [rows * stride][Cc], is the upsampled sequence.
+    const float* src = mel;
+    int rows = N * t_mel, cin = hp.n_mels;
+    for (int i = 0; i < hp.n_upsample; ++i) {
+      const int nc = hp.upsample_strides[i] * Cc;
+      float* dst = w.up[i & 1];
+      pwv::RowGemmBatch rb{m->d_arena + m->off_wup[i], 0, nullptr, 0, dst, 0, nullptr};
+      dim3 grid((nc + 63) / 64, (rows + 63) / 64, 1);
+      pwv::k_row_gemm<true><<<grid, 256, 0, st>>>(src, rb, rows, cin, nc);
+      ++launches;
+      src = dst;
+      rows *= hp.upsample_strides[i];
+      cin = Cc;
+    }
+    // crop: utterance n keeps rows hop/2 .. hop/2 + T - 1 of its t_mel * hop upsampled rows
+    PWV_CUDA(cudaMemcpy2DAsync(w.cproj, sizeof(float) * (size_t)T * Cc, src + (size_t)(hp.hop_length / 2) * Cc,
+                               sizeof(float) * (size_t)t_mel * hp.hop_length * Cc, sizeof(float) * (size_t)T * Cc, N,
+                               cudaMemcpyDeviceToDevice, st));
+  } else {
+    // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
     pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, w.cproj, 0, nullptr};
     const int M = N * t_mel;
     dim3 grid((Cc + 63) / 64, (M + 63) / 64, 1);
@@ -793,9 +871,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     // per-layer conditioning terms of this flow: cbias[b][j] = cproj . [gc_filter|gc_gate] + [bf|bg]
     {
       pwv::RowGemmBatch rb{m->d_arena + m->off_wgc[i], (size_t)Cc * 2 * C, m->d_arena + m->off_bfg[i], (size_t)2 * C,
-                           w.cbias, (size_t)N * t_mel * 2 * C,
+                           w.cbias, (size_t)N * crows * 2 * C,
                            hp.precision == PWV_PREC_FP32 ? nullptr : m->d_arena + m->off_colscale};
-      const int M = N * t_mel;
+      const int M = N * crows;
       if (hp.precision != PWV_PREC_FP32 && m->tc.d_cond) {
         pwv::TcCondParams q;
         size_t zbase = 0;

@@ -26,10 +26,11 @@ def _assert_supported(hp):
         if m.get(key):
             raise NotImplementedError(f"model.{key}={m[key]!r}: normalisers are not on the B200 path "
                                       f"(reference modules.py:263-284); they must be ''")
-    if m.cond_upsample_method != 'repeat':
-        raise NotImplementedError(f"model.cond_upsample_method={m.cond_upsample_method!r}: only 'repeat' "
-                                  f"(reference models.py:127-133) is on the B200 path")
-    strides = [4, 4, 5]   # the reference asserts this even for 'repeat' (models.py:26,106)
+    if m.cond_upsample_method not in ('repeat', 'transposed_conv'):
+        # the reference then conditions on nothing (models.py:134-135: cond = None)
+        raise NotImplementedError(f"model.cond_upsample_method={m.cond_upsample_method!r}: 'repeat' "
+                                  f"(reference models.py:127-133) and 'transposed_conv' (models.py:109-124) are on the B200 path")
+    strides = list(W.UPSAMPLE_STRIDES)   # the reference asserts this even for 'repeat' (models.py:26,106)
     if int(np.prod(strides)) != int(hp.signal.hop_length):
         raise AssertionError(f'prod({strides}) != hop_length {hp.signal.hop_length} (reference models.py:106)')
 
@@ -56,7 +57,7 @@ class PwvModel:
         _lib.check(self.lib.pwv_model_create(ctypes.byref(hparams), ctypes.byref(self._h)))
         n = _lib.check(self.lib.pwv_model_num_variables(self._h))
         name = ctypes.c_char_p()
-        shape = (ctypes.c_int64 * 3)()
+        shape = (ctypes.c_int64 * 4)()
         ndim = ctypes.c_int()
         for i in range(n):
             _lib.check(self.lib.pwv_model_variable(self._h, i, ctypes.byref(name), shape, ctypes.byref(ndim)))

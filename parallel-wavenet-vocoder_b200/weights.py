@@ -14,6 +14,7 @@ import numpy as np
 BODIES = ('scalar', 'shifter')      # body 0 = scaler (scope 'scalar'), body 1 = shifter
 ROOT = 'iaf_vocoder'
 EMA_SUFFIX = '/ExponentialMovingAverage'   # tf.train.ExponentialMovingAverage.average_name(v)
+UPSAMPLE_STRIDES = (4, 4, 5)               # the constant IAFVocoder.__call__ passes (reference models.py:26)
 
 
 def model_dims(hp):
@@ -22,7 +23,9 @@ def model_dims(hp):
                 S=int(m.skip_channels), Cc=int(m.condition_channels), n_mels=int(hp.signal.n_mels),
                 hop=int(hp.signal.hop_length), n_iaf=int(m.n_iaf),
                 dilations=[list(map(int, d)) for d in m.dilations[:int(m.n_iaf)]],
-                use_biases=bool(m.use_biases), use_skip=bool(m.use_skip_connection))
+                use_biases=bool(m.use_biases), use_skip=bool(m.use_skip_connection),
+                cond_upsample=str(m.get('cond_upsample_method', 'repeat') or 'repeat'),
+                upsample_strides=list(UPSAMPLE_STRIDES))
 
 
 def variable_shapes(hp):
@@ -30,7 +33,13 @@ def variable_shapes(hp):
     d = model_dims(hp)
     k, R, D, S, Cc = d['k'], d['R'], d['D'], d['S'], d['Cc']
     shapes = OrderedDict()
-    shapes[f'{ROOT}/cond/dense'] = (1, d['n_mels'], Cc)
+    if d['cond_upsample'] == 'transposed_conv':     # reference models.py:109-124: [1, stride, Cc (out), Cin]
+        cin = d['n_mels']
+        for i, stride in enumerate(d['upsample_strides']):
+            shapes[f'{ROOT}/cond/transposed_conv_{i}_weights'] = (1, stride, Cc, cin)
+            cin = Cc
+    else:
+        shapes[f'{ROOT}/cond/dense'] = (1, d['n_mels'], Cc)
     for i in range(d['n_iaf']):
         for body in BODIES:
             p = f'{ROOT}/iaf{i}/{body}'
@@ -78,6 +87,10 @@ def init_weights(hp, seed=0, bias_std=0.0, gain=1.0, dtype=np.float32):
     for name, shape in variable_shapes(hp).items():
         if len(shape) == 1:
             w = rng.normal(0.0, bias_std, size=shape) if bias_std > 0 else np.zeros(shape)
+        elif len(shape) == 4:            # conv2d_transpose filter [1, width, Cout, Cin]
+            _, width, cout, cin = shape
+            limit = np.sqrt(6.0 / (width * cin + width * cout))
+            w = rng.uniform(-limit, limit, size=shape) * gain
         else:
             k, cin, cout = shape
             limit = np.sqrt(6.0 / (k * cin + k * cout))

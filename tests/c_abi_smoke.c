@@ -10,7 +10,7 @@ int main(void) {
   pwv_model* m = NULL;
   int i, j, n;
   const char* name = NULL;
-  int64_t shape[3];
+  int64_t shape[4];
   int ndim = 0;
   float w[80 * 80];
 

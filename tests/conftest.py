@@ -44,7 +44,10 @@ def load_golden(hp, name):
     g = np.load(os.path.join(ROOT, 'tests', 'golden', name), allow_pickle=False)
     n_layers = [int(v) for v in g['n_layers']]
     dil = [[int(v) for v in row[:n]] for row, n in zip(g['dilations'], n_layers)]
-    hp.set_hparam_dict({'model': {'n_iaf': int(g['n_iaf']), 'dilations': dil}}, case='golden/' + name)
+    model = {'n_iaf': int(g['n_iaf']), 'dilations': dil}
+    if 'cond_upsample_method' in g.files:
+        model['cond_upsample_method'] = str(g['cond_upsample_method'])
+    hp.set_hparam_dict({'model': model}, case='golden/' + name)
     seed, bias_std, gain = g['weight_recipe']
     weights = pkg('weights').init_weights(hp, seed=int(seed), bias_std=float(bias_std), gain=float(gain))
     flat = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in weights.values()])

@@ -9,7 +9,7 @@ in the reference's Python. What they do not pin: TensorFlow's kernels (restated 
 
     python tests/golden/make_golden_from_reference.py
 
-writes tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
+writes tests/golden/ref_tran.npz (cond_upsample_method 'transposed_conv'), tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
 inputs and weights, non-zero biases), tests/golden/ref_flows.npz (a 2-flow graph with per-flow
 outputs) and tests/golden/ref_varlist.txt (the graph's variable names in creation order).
 """
@@ -124,6 +124,22 @@ def main():
     assert err < 1e-12
     np.savez_compressed(os.path.join(HERE, 'ref_skip.npz'), **pack(noise, mel, wav, weights, dil, (44, 0.1, 1.0)))
     ref_hp.model.use_skip_connection = False
+
+    # ---- fixture 4: the same 2-flow graph with cond_upsample_method='transposed_conv' (reference models.py:109-124,
+    #      the reference's own hparams case test/tran)
+    ref_hp.model.cond_upsample_method = 'transposed_conv'
+    my_hp.set_hparam_dict({'model': {'n_iaf': 2, 'dilations': dil, 'cond_upsample_method': 'transposed_conv'}}, case='golden/tran')
+    weights = W.init_weights(my_hp, seed=45, bias_std=0.1, dtype=np.float32)
+    wav, created = run_reference(tf, ref_models, weights, noise, mel)
+    assert created == list(W.variable_shapes(my_hp).keys()), 'variable list / creation order differs (transposed_conv)'
+    ours = O.iaf_vocoder_forward(noise, mel, weights, dil, hop, dtype=np.float64)
+    err = np.abs(ours - wav).max()
+    print('transposed_conv graph: reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (err, np.abs(wav).max()))
+    assert err < 1e-12
+    d = pack(noise, mel, wav, weights, dil, (45, 0.1, 1.0))
+    d['cond_upsample_method'] = np.array('transposed_conv')
+    np.savez_compressed(os.path.join(HERE, 'ref_tran.npz'), **d)
+    ref_hp.model.cond_upsample_method = 'repeat'
     print('wrote ref_small.npz, ref_flows.npz, ref_varlist.txt (%d variables in the default graph)' % len(W.variable_shapes(my_hp.set_hparam_yaml('default'))))
 
 

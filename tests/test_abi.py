@@ -25,13 +25,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(L.EXPORTS) == declared
-    assert lib.pwv_version() == 100
+    assert lib.pwv_version() == 101
 
 
 def test_hparams_struct_matches_header():
     L = pkg('_lib')
-    # 11 scalars + 8 + 8*64 int32
-    assert ctypes.sizeof(L.PwvHparams) == 4 * (11 + 8 + 8 * 64)
+    # 11 scalars + 8 + 8*64 int32, then cond_upsample, n_upsample, upsample_strides[4]
+    assert ctypes.sizeof(L.PwvHparams) == 4 * (11 + 8 + 8 * 64 + 2 + 4)
 
 
 def _create(hp, precision='fp32'):
@@ -49,10 +49,10 @@ def test_model_create_validates(hp):
     assert rc == 0 and h.value
     assert lib.pwv_model_num_variables(h) == 1241
     name = ctypes.c_char_p()
-    shape = (ctypes.c_int64 * 3)()
+    shape = (ctypes.c_int64 * 4)()
     ndim = ctypes.c_int()
     assert lib.pwv_model_variable(h, 0, ctypes.byref(name), shape, ctypes.byref(ndim)) == 0
-    assert name.value == b'iaf_vocoder/cond/dense' and list(shape) == [1, 80, 80] and ndim.value == 3
+    assert name.value == b'iaf_vocoder/cond/dense' and list(shape)[:3] == [1, 80, 80] and ndim.value == 3
     names = []
     for i in range(1241):
         lib.pwv_model_variable(h, i, ctypes.byref(name), shape, ctypes.byref(ndim))

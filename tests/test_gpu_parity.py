@@ -85,7 +85,7 @@ def test_edge_shapes(hp, n, t, precision):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_tran.npz'])
 def test_golden_fixture(hp, name, precision):
     """Committed fixtures produced by executing the reference's own modules.py/models.py under the
     numpy TF stand-in (tests/golden/make_golden_from_reference.py)."""
@@ -294,4 +294,34 @@ def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision):
         if precision == 'f16x3' and n * t <= 8000:
             ref = _oracle(hp, weights, noise, mel)
             assert np.abs(got.cpu().numpy() - ref).max() <= TOL
+        del model
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
+def test_transposed_conv_upsampling(hp, precision):
+    """model.cond_upsample_method = 'transposed_conv' (reference models.py:109-124, the reference's own case
+    test/tran): three conv2d_transpose stages (strides 4, 4, 5) + relu, cropped by hop/2 -- the conditioning then
+    differs at every sample, so the per-layer conditioning terms are full-rate. Against the oracle on the default
+    graph (N=2, T=4000) and on an edge graph; causality of the conditioning path."""
+    W = pkg('weights')
+    for dil, n, t in ((None, 2, 4000), (((1, 512, 2), (256, 1)), 3, 240)):
+        if dil is None:
+            hp.set_hparam_yaml('default')
+            hp.engine.precision = precision
+        else:
+            small_case(hp, dilations=dil, n=n, t=t, precision=precision)
+        hp.model.cond_upsample_method = 'transposed_conv'
+        weights = W.init_weights(hp, seed=6, bias_std=0.1)
+        assert 'iaf_vocoder/cond/transposed_conv_2_weights' in weights and 'iaf_vocoder/cond/dense' not in weights
+        noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=41, noise_seed=42)
+        ref = _oracle(hp, weights, noise, mel)
+        out, model = _run(hp, weights, noise, mel, precision=precision)
+        assert np.abs(out.cpu().numpy() - ref).max() <= TOL, (dil, n, t)
+        if dil is None:     # changing mel frames after (t0 + hop/2) // hop leaves wav[:t0] bit-identical
+            t0 = 2000
+            mel2 = mel.copy()
+            mel2[:, (t0 + 40) // 80 + 1:, :] *= -1.0
+            out2 = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel2).cuda())
+            assert torch.equal(out2[:, :t0], out[:, :t0]) and not torch.equal(out2[:, t0:], out[:, t0:])
         del model
