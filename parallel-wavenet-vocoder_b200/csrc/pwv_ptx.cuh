@@ -95,6 +95,9 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) { asm volati
 
 // named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// producer side of a named barrier: counts this warp's 32 threads in and moves on (the warps that bar.sync on
+// the same id observe the arriving threads' earlier writes when the barrier completes)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ----------------------------------------------------------------------------- TMEM
 // Allocate `ncols` (power of two >= 32) TMEM columns; one full warp calls this; the base address

@@ -873,6 +873,7 @@ struct TcFlowParams {
   long long* trace;         // debug timeline of CTA 0 for layer trace_layer (or nullptr)
   int trace_layer;
   int stagger;              // see the producers
+  int rotate;               // 1: rotate the tile-to-CTA assignment from layer to layer (see cta_of in the kernel)
 };
 
 struct TcFlowBarriers {
@@ -887,7 +888,21 @@ struct TcFlowBarriers {
     if (p.trace && blockIdx.x == 0 && (l) == p.trace_layer && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
   } while (0)
 
-template <bool BF16, bool SPLIT, bool PK = false>
+// QUIET hand-offs (template flag): the role-to-role hand-offs inside a tile slot go through hardware named
+// barriers instead of mbarriers that the waiting warps poll. Measured reason (ncu source counters of the polling
+// version, profiles/r1_flow_kernel.txt): 40 % of all executed warp instructions were try_wait / branch / yield
+// of polling warps (2,200 polls per tile), issued on the same four schedulers as the epilogue arithmetic.
+//   workers -> MMA issuer  (operands converted, z written):   workers bar.arrive, the issuer warp bar.sync
+//   MMA issuer -> workers  (accumulator complete):            the issuer's elected thread is the ONLY poller of the
+//                                                             tcgen05.commit mbarrier, then its warp bar.arrive,
+//                                                             the workers bar.sync (blocked, not polling)
+//   workers -> producer    (x[t-d] boxes converted, output copied out): workers bar.arrive, producer warp bar.sync
+// Only completions of the async units (TMA bytes landed, tcgen05.commit) still need mbarriers. A named barrier
+// is reused tile after tile: every arrival of tile j+1 is causally after the completion of tile j's barrier.
+constexpr int TCF_NB_AREADY = 1, TCF_NB_ZREADY = 3, TCF_NB_D1 = 5, TCF_NB_D2 = 7, TCF_NB_XFREE = 9, TCF_NB_YFREE = 11;   // + slot
+constexpr int TCF_NB_COUNT = 256 + 32;         // the slot's 8 worker warps + the one issuer / producer warp
+
+template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const __grid_constant__ TcFlowParams p) {
   using namespace ptx;
@@ -900,6 +915,19 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
   const int tiles_body = p.N * p.tiles_per_utt;
   const int n_local = (tiles_body > cta_in_body) ? (tiles_body - cta_in_body + ctas_per_body - 1) / ctas_per_body : 0;
   const int L = p.L;
+  // Tile-to-CTA assignment. Layer l's tiles c, c + P, c + 2P, ... (P = CTAs per body) belong to the CTA whose
+  // virtual index for that layer is c. With tiles_body = a P + r the r lowest virtual indices carry a + 1 tiles;
+  // a fixed assignment makes the same r CTAs the critical path of EVERY layer (c2: 14 vs 13 tiles, 3.6 %).
+  // Rotating the virtual index by r per layer slides the window of long CTAs once around the grid, so that over
+  // the flow every CTA walks the same number of tiles (+-1). The per-tile flags make any assignment correct.
+  // Only when every CTA keeps >= 1 tile per slot in every layer (the weight hand-over counts on both slots).
+  const int rot = (p.rotate && tiles_body >= 2 * ctas_per_body) ? tiles_body % ctas_per_body : 0;
+  auto cta_of = [&](int l) { return rot ? (cta_in_body + l * rot) % ctas_per_body : cta_in_body; };
+  auto tiles_in = [&](int l, int s) {            // tiles of slot s of this CTA in layer l
+    const int c = cta_of(l);
+    const int nl = (tiles_body > c) ? (tiles_body - c + ctas_per_body - 1) / ctas_per_body : 0;
+    return (nl + 1 - s) / 2;
+  };
 
   pdl_launch_dependents();
   if (warp == TC_MMA_WARP) {
@@ -930,7 +958,100 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
+  if (QUIET && (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1)) {
+    // ======================= MMA issuers, QUIET hand-offs: the whole warp walks the tile list (named barriers are
+    // warp-wide), the elected thread issues, loads the weights and polls the tcgen05.commit barriers =======================
+    const int s = warp - TC_MMA_WARP;
+    const bool leader = elect_one();
+    const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
+    const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
+    constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
+    const uint32_t tD = tmem + s * 256;
+    const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+    uint32_t it = 0;
+    for (int l = 0; l < L && n_local > 0; ++l) {
+      const bool last_layer = l == L - 1;
+      const int tiles_s = tiles_in(l, s);
+      const uint8_t* img = p.images + ((size_t)body * L + l) * TC_IMAGE_BYTES;
+      if (leader) {
+        if (s == 0) {
+          if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
+          mbar_arrive_expect_tx(&bars->w1_ready, 2 * TC_W1_BYTES + TCF_TAIL_BYTES);
+          for (int off = 0; off < 2 * TC_W1_BYTES; off += 16384) bulk_g2s(smem + off, img + off, 16384, &bars->w1_ready);
+          bulk_g2s(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES, img + TC_OFF_BD, TCF_TAIL_BYTES, &bars->w1_ready);
+        }
+        if (tiles_s == 0) {
+          mbar_wait(&bars->w1_ready, l & 1);
+          mbar_arrive(&bars->w1_free);
+          if (!last_layer) {
+            mbar_wait(&bars->w2_ready, l & 1);
+            mbar_arrive(&bars->w2_free);
+          }
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < tiles_s; ++j, ++it) {
+        named_bar_sync(TCF_NB_AREADY + s, TCF_NB_COUNT);           // the slot's A1 operands are in TMEM
+        if (leader) {
+          if (j == 0) mbar_wait(&bars->w1_ready, l & 1);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TCF_TRACE(2, l, j, s * 8 + 0);
+          uint32_t acc = 0;
+          if (SPLIT) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks, acc = 1)
+              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks, acc = 1)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+          mma_commit(&bars->d1_ready[s]);
+          if (j == tiles_s - 1) mma_commit(&bars->w1_free);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+          TCF_TRACE(2, l, j, s * 8 + 1);
+          if (!last_layer && s == 0 && j == 0) {
+            if (l > 0) mbar_wait(&bars->w2_free, (l - 1) & 1);
+            mbar_arrive_expect_tx(&bars->w2_ready, 2 * TC_W2_BYTES);
+            bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
+          }
+          mbar_wait(&bars->d1_ready[s], it & 1);                   // GEMM1 complete ...
+        }
+        __syncwarp();
+        named_bar_arrive(TCF_NB_D1 + s, TCF_NB_COUNT);             // ... relayed to the slot's workers
+        if (last_layer) continue;
+        named_bar_sync(TCF_NB_ZREADY + s, TCF_NB_COUNT);           // z is in TMEM
+        if (leader) {
+          if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TCF_TRACE(2, l, j, s * 8 + 2);
+          uint32_t acc = 0;
+          if (SPLIT) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks, acc = 1)
+              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks, acc = 1)
+            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+          mma_commit(&bars->d2_ready[s]);
+          if (j == tiles_s - 1) mma_commit(&bars->w2_free);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+          TCF_TRACE(2, l, j, s * 8 + 3);
+          mbar_wait(&bars->d2_ready[s], it & 1);
+        }
+        __syncwarp();
+        named_bar_arrive(TCF_NB_D2 + s, TCF_NB_COUNT);
+      }
+    }
+  } else if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
     // ======================= MMA issuers (one per tile slot); slot 0's also hands the weights over =======================
     if (elect_one() && n_local > 0) {
       const int s = warp - TC_MMA_WARP;
@@ -939,10 +1060,10 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
       const uint32_t tD = tmem + s * 256;
       const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-      const int tiles_s = (n_local + 1 - s) / 2;
       uint32_t it = 0;                                  // tiles of this slot so far (barrier phase)
       for (int l = 0; l < L; ++l) {
         const bool last_layer = l == L - 1;
+        const int tiles_s = tiles_in(l, s);
         const uint8_t* img = p.images + ((size_t)body * L + l) * TC_IMAGE_BYTES;
         if (s == 0) {       // W1 + bias/scale tail of layer l, once BOTH slots' last GEMM1 of layer l-1 has completed
           if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
@@ -1014,22 +1135,24 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
     __syncwarp();
   } else if (warp >= TC_TMA_WARP) {
     // ======================= TMA producers (one per tile slot) =======================
-    if (elect_one()) {
+    // (QUIET: the whole warp walks the tile list because named barriers are warp-wide; `leader` does the work)
+    if (QUIET || elect_one()) {
       const int s = warp - TC_TMA_WARP;
+      const bool leader = QUIET ? elect_one() : true;
       tma_prefetch_desc(&map0);
       tma_prefetch_desc(&map1);
       uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
-      const int tiles_s = (n_local + 1 - s) / 2;
-      const int Q = L * tiles_s;                        // this slot's tile list: q = l * tiles_s + j
-      auto coords = [&](int j, int& n, int& t0) {
-        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+      // this slot's tile list: layer after layer, tiles_in(l, s) tiles each (the same count in every layer unless
+      // the assignment rotates; a slot without tiles in layer 0 has none at all)
+      auto coords = [&](int l, int j, int& n, int& t0) {
+        const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
         n = tile / p.tiles_per_utt;
         t0 = (tile % p.tiles_per_utt) * TC_TM;
       };
       auto map_of = [&](int l) { return ((p.cur0 + l) & 1) ? &map1 : &map0; };
       auto issue_x = [&](int l, int j) {
         int n, t0;
-        coords(j, n, t0);
+        coords(l, j, n, t0);
         const int d = p.dilation[l];
         mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
         tma_load_3d(st, map_of(l), 0, t0 - d, body * p.N + n, &bars->x_full[s]);
@@ -1037,7 +1160,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       };
       auto issue_y = [&](int l, int j) {     // x[t] boxes + the conditioning rows of the frames the tile touches
         int n, t0;
-        coords(j, n, t0);
+        coords(l, j, n, t0);
         mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
         tma_load_3d(st + 2 * TC_BOX_BYTES, map_of(l), 0, t0, body * p.N + n, &bars->y_full[s]);
         tma_load_3d(st + 3 * TC_BOX_BYTES, map_of(l), 32, t0, body * p.N + n, &bars->y_full[s]);
@@ -1053,7 +1176,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       auto tiles_ready = [&](int l, int j) -> bool {
         if (l == 0) return true;
         int n, t0;
-        coords(j, n, t0);
+        coords(l, j, n, t0);
         const int d = p.dilation[l], dp = p.dilation[l - 1];
         const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
         const int* f = p.flags + ((size_t)(l - 1) * 2 + body) * tiles_body + (size_t)n * p.tiles_per_utt;
@@ -1068,30 +1191,71 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         return true;
       };
       auto publish = [&](int l, int j) {   // after y_free[s]: all 256 workers of the slot have stored the tile's output
-        const int tile = cta_in_body + (s + 2 * j) * ctas_per_body;
+        const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
         fence_acq_rel_gpu();               // (release, cumulative over the workers' stores observed through y_free)
         st_relaxed_gpu(p.flags + ((size_t)l * 2 + body) * tiles_body + tile, 1);
       };
-      pdl_wait_prior_grid();      // the flow's input (k_front) and everything before it is complete
-      // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0), when
-      // its first GEMM1 has completed (1) or when its first gate phase is through (2)
-      if (s == 1 && n_local > 0) {
-        if (p.stagger == 1) mbar_wait(&bars->d1_ready[0], 0);
-        else if (p.stagger == 2) mbar_wait(&bars->z_ready[0], 0);
-        else mbar_wait(&bars->y_full[0], 0);
+      if (leader) {
+        pdl_wait_prior_grid();      // the flow's input (k_front) and everything before it is complete
+        // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0), when
+        // its first GEMM1 has completed (1) or when its first gate phase is through (2; an mbarrier only without QUIET)
+        if (s == 1 && n_local > 0) {
+          if (p.stagger == 1 || (QUIET && p.stagger == 2)) mbar_wait(&bars->d1_ready[0], 0);
+          else if (p.stagger == 2) mbar_wait(&bars->z_ready[0], 0);
+          else mbar_wait(&bars->y_full[0], 0);
+        }
+        if (tiles_in(0, s) > 0) {
+          issue_x(0, 0);
+          issue_y(0, 0);
+        }
       }
-      if (Q > 0) {
-        issue_x(0, 0);
-        issue_y(0, 0);
-      }
+      int l = 0, j = 0, tiles_l = tiles_in(0, s);       // the tile in flight and its layer's tile count
+      uint32_t q = 0;                                   // tiles of this slot so far (barrier phase)
+      if (QUIET) {
+        // Same protocol as below; the "boxes converted" / "output copied out" events are named barriers the
+        // slot's workers arrive on (also for the slot's very last tile, so that no arrival is left pending).
+        __syncwarp();
+        while (tiles_l > 0) {
+          const int ln = (j + 1 == tiles_l) ? l + 1 : l, jn = (j + 1 == tiles_l) ? 0 : j + 1;     // the slot's next tile
+          const bool more = ln < L;
+          named_bar_sync(TCF_NB_XFREE + s, TCF_NB_COUNT);
+          bool early = false;
+          if (leader && more) {
+            early = tiles_ready(ln, jn);
+            if (early) {
+              issue_x(ln, jn);
+              TCF_TRACE(3, l, j, s * 8 + 0);
+            }
+          }
+          __syncwarp();
+          named_bar_sync(TCF_NB_YFREE + s, TCF_NB_COUNT);
+          if (leader && more) {
+            if (early) {
+              issue_y(ln, jn);
+              if (l < L - 1) publish(l, j);
+            } else {
+              if (l < L - 1) publish(l, j);
+              while (!tiles_ready(ln, jn)) {
+              }
+              issue_x(ln, jn);
+              issue_y(ln, jn);
+            }
+            TCF_TRACE(3, l, j, s * 8 + 2);
+          }
+          __syncwarp();
+          if (!more) break;
+          if (ln != l) tiles_l = tiles_in(ln, s);
+          l = ln;
+          j = jn;
+        }
+      } else
       // A tile is published as soon as it is stored, NEVER after a wait for other CTAs' tiles (two CTAs whose next
       // tiles need each other's current tiles would wait forever): the inputs of the slot's next tile are only
       // PROBED early (to prefetch its x[t-d] boxes, the normal case inside a layer); if they are not all there yet
       // the blocking wait comes after this tile's publication.
-      for (int q = 0; q < Q; ++q) {
-        const int l = q / tiles_s, j = q - l * tiles_s;
-        if (q + 1 == Q) break;                          // (last layer: nothing to publish, nothing to refill)
-        const int ln = (q + 1) / tiles_s, jn = (q + 1) - ln * tiles_s;
+      for (; tiles_l > 0; ++q) {
+        const int ln = (j + 1 == tiles_l) ? l + 1 : l, jn = (j + 1 == tiles_l) ? 0 : j + 1;       // the slot's next tile
+        if (ln == L) break;                             // (last layer: nothing to publish, nothing to refill)
         mbar_wait(&bars->x_free[s], q & 1);             // the slot's x[t-d] boxes have been converted
         const bool early = tiles_ready(ln, jn);
         if (early) {
@@ -1110,6 +1274,9 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
           issue_y(ln, jn);
         }
         TCF_TRACE(3, l, j, s * 8 + 2);
+        if (ln != l) tiles_l = tiles_in(ln, s);
+        l = ln;
+        j = jn;
       }
     }
     __syncwarp();
@@ -1124,11 +1291,11 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
     uint8_t* my_x = stage + half * TC_BOX_BYTES + r * 128;
     uint8_t* my_y = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
     const bool tracer = (warp & 7) == 0 && lane == 0;
-    const int tiles_s = (n_local + 1 - slot) / 2;
     uint32_t it = 0;
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       const bool last_layer = l == L - 1;
+      const int tiles_s = tiles_in(l, slot), cta_l = cta_of(l);
       const float* tail = reinterpret_cast<const float*>(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES);
       const float* bd_s = tail + half * 32;
       const float* cbias_l = p.cbias + ((size_t)body * L + l) * p.N * p.t_mel * 128;
@@ -1136,7 +1303,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       float sf = 0.f, sg = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int j = 0; j < tiles_s; ++j, ++it) {
-        const int tile = cta_in_body + (slot + 2 * j) * ctas_per_body;
+        const int tile = cta_l + (slot + 2 * j) * ctas_per_body;
         const int n = tile / p.tiles_per_utt, t = (tile % p.tiles_per_utt) * TC_TM + r;
         const uint32_t par = it & 1;
 
@@ -1144,14 +1311,16 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         mbar_wait(&bars->x_full[slot], par);
         if (tracer) TCF_TRACE(slot, l, j, 1);
         tc_prep<BF16, SPLIT, PK>(my_x, r, tAhi + half * 16, tAlo + half * 16);
-        mbar_arrive(&bars->x_free[slot]);
+        if (QUIET) named_bar_arrive(TCF_NB_XFREE + slot, TCF_NB_COUNT);
+        else mbar_arrive(&bars->x_free[slot]);
         if (tracer) TCF_TRACE(slot, l, j, 2);
         mbar_wait(&bars->y_full[slot], par);
         if (tracer) TCF_TRACE(slot, l, j, 3);
         tc_prep<BF16, SPLIT, PK>(my_y, r, tAhi + 32 + half * 16, tAlo + 32 + half * 16);
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&bars->a_ready[slot]);
+        if (QUIET) named_bar_arrive(TCF_NB_AREADY + slot, TCF_NB_COUNT);
+        else mbar_arrive(&bars->a_ready[slot]);
         if (tracer) TCF_TRACE(slot, l, j, 4);
 
         if (j == 0) {                     // the layer's scales / dense bias arrive with W1
@@ -1168,7 +1337,8 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         }
 
         // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
-        mbar_wait(&bars->d1_ready[slot], par);
+        if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);     // (the slot's issuer saw GEMM1's commit)
+        else mbar_wait(&bars->d1_ready[slot], par);
         tc_fence_after_sync();
         if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
         if (tracer) TCF_TRACE(slot, l, j, 5);
@@ -1198,11 +1368,13 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         if (!last_layer) {
           tmem_wait_st();
           tc_fence_before_sync();
-          mbar_arrive(&bars->z_ready[slot]);
+          if (QUIET) named_bar_arrive(TCF_NB_ZREADY + slot, TCF_NB_COUNT);
+          else mbar_arrive(&bars->z_ready[slot]);
           if (tracer) TCF_TRACE(slot, l, j, 6);
 
           // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] half row)
-          mbar_wait(&bars->d2_ready[slot], par);
+          if (QUIET) named_bar_sync(TCF_NB_D2 + slot, TCF_NB_COUNT);
+          else mbar_wait(&bars->d2_ready[slot], par);
           tc_fence_after_sync();
           if (tracer) TCF_TRACE(slot, l, j, 7);
           uint32_t dr[2][16];
@@ -1246,7 +1418,8 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         }
         if (tracer) TCF_TRACE(slot, l, j, 11);
         tc_fence_before_sync();
-        mbar_arrive(&bars->y_free[slot]);
+        if (QUIET) named_bar_arrive(TCF_NB_YFREE + slot, TCF_NB_COUNT);
+        else mbar_arrive(&bars->y_free[slot]);
         if (tracer) TCF_TRACE(slot, l, j, 8);
       }
     }

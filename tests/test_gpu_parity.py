@@ -268,10 +268,15 @@ def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
-def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision):
+@pytest.mark.parametrize('quiet,rotate', [(0, 0), (1, 0), (1, 1)])
+def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision, quiet, rotate):
     """k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
     the same tile pipeline as the one-launch-per-layer path (PWV_TC_FLOW=0): outputs must be BIT-identical,
-    including one-tile CTAs (idle second slot), single-layer flows (no GEMM2 at all), d >= T and ragged tiles."""
+    including one-tile CTAs (idle second slot), single-layer flows (no GEMM2 at all), d >= T and ragged tiles.
+    Covered for both hand-off styles (PWV_TC_QUIET: polled mbarriers / named barriers) and with the per-layer
+    rotation of the tile-to-CTA assignment (PWV_TC_ROTATE)."""
+    monkeypatch.setenv('PWV_TC_QUIET', str(quiet))
+    monkeypatch.setenv('PWV_TC_ROTATE', str(rotate))
     W = pkg('weights')
     cases = [(None, 2, 4000), (((1, 512, 2), (256, 1)), 5, 1040), (((1, 512, 2), (256, 1)), 1, 80), (((1,), (2, 4), (128,)), 3, 2000),
              (((1, 2, 4, 8, 16, 32, 64, 128, 256, 512) * 3,), 4, 8000), (None, 8, 16000)]
