@@ -349,7 +349,7 @@ def main():
         with open(tpath) as fh:
             traffic = json.load(fh).get(precision, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
-                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layer k_layer_tc (tcgen05, both bodies per launch)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
+                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layers in k_flow_tc (tcgen05; one persistent launch per flow, both bodies; figures per gated layer)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
                 'bytes_per_launch': n_gated * bytes_per_layer / max(layer_n, 1), 'avg_launch_us': layer_s * 1e6 / max(layer_n, 1),
                 'isolated_launch_us': float(np.median(iso_ms)) * 1e3 / max(iso_n, 1),
                 'frac_isolated': n_gated * bytes_per_layer / (float(np.median(iso_ms)) * 1e-3) / 1e9 / pk['hbm'],
@@ -358,7 +358,7 @@ def main():
                 'tflops_fp32_equiv': 2 * n_gated * mac_per_layer / layer_s / 1e12,
                 'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); avg_launch_us = CUDA events around each flow\'s chain of '
                         'gated-layer launches as launched in the timed steps / launches; isolated_launch_us = every launch bracketed (serialised, what ncu lists); '
-                        'the kernel is bound by tensor/MUFU/issue, not HBM: see DESIGN.md'}
+                        'the kernel is bound by the length of the per-tile chain with two tiles resident per SM (TMEM / shared-memory capacity), no unit saturated: see DESIGN.md 7'}
 
     # ---- e2e: host buffers in, host buffer out, copies inside the timed region.
     #      N = 1: the C-ABI call pwv_forward_host (H2D + kernels + D2H + sync inside the call).
