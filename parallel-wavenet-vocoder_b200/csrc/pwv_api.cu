@@ -106,6 +106,7 @@ struct pwv_model {
   int tc_stagger = 0;            // PWV_TC_STAGGER (A/B runs): how far slot 1 starts behind slot 0 in k_flow_tc
   bool use_flow = true;          // one persistent launch per flow (k_flow_tc); PWV_TC_FLOW=0: one launch per layer
   bool tc_rotate = true;         // k_flow_tc: tile-to-CTA assignment rotates from layer to layer (PWV_TC_ROTATE=0: fixed)
+  bool tc_hoist = false;         // k_flow_tc (QUIET form): epilogue loads hoisted above the waits, 8-channel gate chunks (PWV_TC_HOIST)
   bool tc_quiet = true;          // k_flow_tc hand-offs through named barriers instead of polled mbarriers (PWV_TC_QUIET=0: polled)
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
@@ -214,6 +215,8 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -292,6 +295,7 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (const char* v = getenv("PWV_TC_STAGGER")) m->tc_stagger = atoi(v);
   if (const char* v = getenv("PWV_TC_QUIET")) m->tc_quiet = atoi(v) != 0;
   if (const char* v = getenv("PWV_TC_ROTATE")) m->tc_rotate = atoi(v) != 0;
+  if (const char* v = getenv("PWV_TC_HOIST")) m->tc_hoist = atoi(v) != 0;
   if (const char* v = getenv("PWV_TC_VARIANT")) {
     const int k = atoi(v);
     if (k >= 0 && k <= 1) m->tc_variant = k;
@@ -734,6 +738,8 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     for (int j = 0; j < L; ++j) q.dilation[j] = hp.dilations[flow][j];
     q.stagger = m->tc_stagger;
     q.rotate = m->tc_rotate ? 1 : 0;
+    q.debug_unsafe = getenv("PWV_TC_DEBUG_UNSAFE") ? atoi(getenv("PWV_TC_DEBUG_UNSAFE")) : 0;   // timing experiments only
+    q.e1_lock = (m->tc_quiet && getenv("PWV_TC_E1LOCK") && atoi(getenv("PWV_TC_E1LOCK"))) ? 1 : 0;
     q.trace = m->trace; q.trace_layer = m->trace ? m->trace_launch - (int)(layer_base / 2) : -1;
     if (m->profiling == 2) PWV_PROF_MARK(m, st);
     cudaLaunchConfig_t cfg = {};
@@ -746,7 +752,10 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = m->use_pdl ? 1 : 0;
-    if (m->tc_quiet) {
+    if (m->tc_quiet && m->tc_hoist) {
+      if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true, true>, maps[0], maps[1], q));
+      else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true, true>, maps[0], maps[1], q));
+    } else if (m->tc_quiet) {
       if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true>, maps[0], maps[1], q));
       else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true>, maps[0], maps[1], q));
     } else if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false>, maps[0], maps[1], q));

@@ -874,6 +874,8 @@ struct TcFlowParams {
   int trace_layer;
   int stagger;              // see the producers
   int rotate;               // 1: rotate the tile-to-CTA assignment from layer to layer (see cta_of in the kernel)
+  int e1_lock;              // 1 (QUIET only, A/B): the two slots' gate phases (epilogue 1, MUFU-heavy) never overlap
+  int debug_unsafe;         // TIMING EXPERIMENTS ONLY, results undefined: 1 = flags without the gpu-scope fences, 2 = no flags at all
 };
 
 struct TcFlowBarriers {
@@ -881,6 +883,7 @@ struct TcFlowBarriers {
   uint64_t x_full[2], y_full[2], c_full[2], x_free[2], y_free[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
   int mma_lock;
+  int e1_lock;
 };
 
 #define TCF_TRACE(role, l, j, k)                                                                    \
@@ -902,7 +905,13 @@ struct TcFlowBarriers {
 constexpr int TCF_NB_AREADY = 1, TCF_NB_ZREADY = 3, TCF_NB_D1 = 5, TCF_NB_D2 = 7, TCF_NB_XFREE = 9, TCF_NB_YFREE = 11;   // + slot
 constexpr int TCF_NB_COUNT = 256 + 32;         // the slot's 8 worker warps + the one issuer / producer warp
 
-template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false>
+// HOIST (template flag, needs nothing else): the same per-element arithmetic with the loads moved off the chain.
+// The phase traces show the gate phase at 2x its MUFU bound even when the other slot is idle (mutual-exclusion
+// experiment, profiles/r1_ab_e1lock.txt): each 16-channel round trip starts with a tcgen05.ld (~230 cycles) and
+// the conditioning-row loads, all exposed. Here epilogue 1 walks four 8-channel chunks with the next chunk's
+// accumulators in flight during the current chunk's arithmetic, chunk 0's conditioning rows are read before
+// the wait for GEMM1, and epilogue 2 reads its x[t] row before the wait for GEMM2.
+template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false, bool HOIST = false>
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const __grid_constant__ TcFlowParams p) {
   using namespace ptx;
@@ -948,6 +957,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         mbar_init(&bars->d2_ready[s], 1);
       }
       bars->mma_lock = 0;
+      bars->e1_lock = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -1019,12 +1029,14 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
             bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
           }
           mbar_wait(&bars->d1_ready[s], it & 1);                   // GEMM1 complete ...
+          if (p.e1_lock && !last_layer) tc_lock<true>(&bars->e1_lock);    // (... and the other slot is out of its gate phase)
         }
         __syncwarp();
         named_bar_arrive(TCF_NB_D1 + s, TCF_NB_COUNT);             // ... relayed to the slot's workers
         if (last_layer) continue;
         named_bar_sync(TCF_NB_ZREADY + s, TCF_NB_COUNT);           // z is in TMEM
         if (leader) {
+          if (p.e1_lock) tc_unlock<true>(&bars->e1_lock);
           if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
           tc_lock<SPLIT>(&bars->mma_lock);
           tc_fence_after_sync();
@@ -1174,7 +1186,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       };
       // the tiles of layer l-1 that tile j of layer l reads or whose reads it overwrites (see k_layer_tc): published?
       auto tiles_ready = [&](int l, int j) -> bool {
-        if (l == 0) return true;
+        if (l == 0 || p.debug_unsafe == 2) return true;
         int n, t0;
         coords(l, j, n, t0);
         const int d = p.dilation[l], dp = p.dilation[l - 1];
@@ -1186,12 +1198,15 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         const int a = ld_relaxed_gpu(f + k), b = ld_relaxed_gpu(f + k1), c = ld_relaxed_gpu(f + k2);
         const int d4 = ld_relaxed_gpu(f + k3), e = ld_relaxed_gpu(f + k4);
         if (!(a & b & c & d4 & e)) return false;
+        if (p.debug_unsafe) return true;
         fence_acq_rel_gpu();            // (acquire: the published tiles' rows are visible ...)
         fence_proxy_async_global();     // (... to the TMA loads issued next)
         return true;
       };
       auto publish = [&](int l, int j) {   // after y_free[s]: all 256 workers of the slot have stored the tile's output
         const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
+        if (p.debug_unsafe == 2) return;
+        if (!p.debug_unsafe)
         fence_acq_rel_gpu();               // (release, cumulative over the workers' stores observed through y_free)
         st_relaxed_gpu(p.flags + ((size_t)l * 2 + body) * tiles_body + tile, 1);
       };
@@ -1337,32 +1352,68 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         }
 
         // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
-        if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);     // (the slot's issuer saw GEMM1's commit)
-        else mbar_wait(&bars->d1_ready[slot], par);
-        tc_fence_after_sync();
-        if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
-        if (tracer) TCF_TRACE(slot, l, j, 5);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t fr[16], gr[16];
-          tmem_ld16(tD + half * 32 + c * 16, fr);
-          tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
+        if (HOIST) {
+          if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);        // (landed with the x[t] boxes, long ago)
+          float4 cf[2] = {cb[0], cb[1]}, cg[2] = {cb[16], cb[17]};        // chunk 0's conditioning rows, before the wait
+          if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);
+          else mbar_wait(&bars->d1_ready[slot], par);
+          tc_fence_after_sync();
+          if (tracer) TCF_TRACE(slot, l, j, 5);
+          uint32_t fa[8], ga[8], fb[8], gb[8];
+          tmem_ld8(tD + half * 32, fa);
+          tmem_ld8(tD + 64 + half * 32, ga);
           tmem_wait_ld();
-          if (tracer) TCF_TRACE(slot, l, j, 12 + c);
-          float z[16];
-          tc_gate<BF16, PK, 16>(fr, gr, cb + c * 4, cb + 16 + c * 4, sf, sg, z);
-          if (last_layer) {               // z itself is the output (x[t] is dead)
+          if (tracer) TCF_TRACE(slot, l, j, 12);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-          } else {
-            uint32_t hi[8], lo[8];
-            float v0[8], v1[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
-            split8x<BF16, SPLIT, PK>(v0, hi, lo);
-            split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
-            tmem_st8(tAhi + half * 16 + c * 8, hi);
-            if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+          for (int c = 0; c < 4; ++c) {        // 8 channels per chunk; chunk c+1's accumulators load during chunk c's arithmetic
+            uint32_t (&fr)[8] = (c & 1) ? fb : fa, (&gr)[8] = (c & 1) ? gb : ga;
+            if (c < 3) {
+              tmem_ld8(tD + half * 32 + (c + 1) * 8, (c & 1) ? fa : fb);
+              tmem_ld8(tD + 64 + half * 32 + (c + 1) * 8, (c & 1) ? ga : gb);
+            }
+            float z[8];
+            tc_gate<BF16, PK, 8>(fr, gr, cf, cg, sf, sg, z);
+            if (c < 3) { cf[0] = cb[(c + 1) * 2]; cf[1] = cb[(c + 1) * 2 + 1]; cg[0] = cb[16 + (c + 1) * 2]; cg[1] = cb[16 + (c + 1) * 2 + 1]; }
+            if (last_layer) {
+              *box_chunk(my_y, r, c * 2) = make_float4(z[0], z[1], z[2], z[3]);
+              *box_chunk(my_y, r, c * 2 + 1) = make_float4(z[4], z[5], z[6], z[7]);
+            } else {
+              uint32_t hi[4], lo[4];
+              split8x<BF16, SPLIT, PK>(z, hi, lo);
+              tmem_st4(tAhi + half * 16 + c * 4, hi);
+              if (SPLIT) tmem_st4(tAlo + half * 16 + c * 4, lo);
+            }
+            if (c < 3) tmem_wait_ld();
+            if (c == 1 && tracer) TCF_TRACE(slot, l, j, 13);
+          }
+        } else {
+          if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);     // (the slot's issuer saw GEMM1's commit)
+          else mbar_wait(&bars->d1_ready[slot], par);
+          tc_fence_after_sync();
+          if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
+          if (tracer) TCF_TRACE(slot, l, j, 5);
+  #pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t fr[16], gr[16];
+            tmem_ld16(tD + half * 32 + c * 16, fr);
+            tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
+            tmem_wait_ld();
+            if (tracer) TCF_TRACE(slot, l, j, 12 + c);
+            float z[16];
+            tc_gate<BF16, PK, 16>(fr, gr, cb + c * 4, cb + 16 + c * 4, sf, sg, z);
+            if (last_layer) {               // z itself is the output (x[t] is dead)
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+            } else {
+              uint32_t hi[8], lo[8];
+              float v0[8], v1[8];
+  #pragma unroll
+              for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
+              split8x<BF16, SPLIT, PK>(v0, hi, lo);
+              split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
+              tmem_st8(tAhi + half * 16 + c * 8, hi);
+              if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+            }
           }
         }
         if (!last_layer) {
@@ -1373,6 +1424,11 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
           if (tracer) TCF_TRACE(slot, l, j, 6);
 
           // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] half row)
+          float4 xrow[8];
+          if (HOIST) {                    // my x[t] half row, before the wait for GEMM2
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xrow[q] = *box_chunk(my_y, r, q);
+          }
           if (QUIET) named_bar_sync(TCF_NB_D2 + slot, TCF_NB_COUNT);
           else mbar_wait(&bars->d2_ready[slot], par);
           tc_fence_after_sync();
@@ -1385,7 +1441,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(bd_s + q * 4);
-            const float4 xv = *box_chunk(my_y, r, q);
+            const float4 xv = HOIST ? xrow[q] : *box_chunk(my_y, r, q);
             const uint32_t* d = &dr[q >> 2][(q & 3) * 4];
             float4 o;
             if (PK) {
