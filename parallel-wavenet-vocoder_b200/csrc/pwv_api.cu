@@ -105,9 +105,9 @@ struct pwv_model {
   bool use_flags = true;         // tile handshake between consecutive gated layers (PWV_NO_TILE_FLAGS=1: off)
   int tc_stagger = 0;            // PWV_TC_STAGGER (A/B runs): how far slot 1 starts behind slot 0 in k_flow_tc
   bool use_flow = true;          // one persistent launch per flow (k_flow_tc); PWV_TC_FLOW=0: one launch per layer
-  bool tc_rotate = true;         // k_flow_tc: tile-to-CTA assignment rotates from layer to layer (PWV_TC_ROTATE=0: fixed)
-  bool tc_hoist = false;         // k_flow_tc (QUIET form): epilogue loads hoisted above the waits, 8-channel gate chunks (PWV_TC_HOIST)
-  bool tc_quiet = true;          // k_flow_tc hand-offs through named barriers instead of polled mbarriers (PWV_TC_QUIET=0: polled)
+  bool tc_rotate = false;        // k_flow_tc: tile-to-CTA assignment rotates from layer to layer (PWV_TC_ROTATE=1; A/B switch)
+  int tc_seg = 0;                // k_flow_tc: gated layers per launch (PWV_TC_SEG; 0 = by job size, see launch_layers_tc)
+  bool tc_quiet = false;         // EXPERIMENTAL (PWV_TC_QUIET=1): 512-thread form of k_flow_tc, helper work folded into the slots' head warps
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1 in the environment overrides (A/B runs)
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
@@ -215,8 +215,6 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -295,7 +293,7 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (const char* v = getenv("PWV_TC_STAGGER")) m->tc_stagger = atoi(v);
   if (const char* v = getenv("PWV_TC_QUIET")) m->tc_quiet = atoi(v) != 0;
   if (const char* v = getenv("PWV_TC_ROTATE")) m->tc_rotate = atoi(v) != 0;
-  if (const char* v = getenv("PWV_TC_HOIST")) m->tc_hoist = atoi(v) != 0;
+  if (const char* v = getenv("PWV_TC_SEG")) m->tc_seg = atoi(v);
   if (const char* v = getenv("PWV_TC_VARIANT")) {
     const int k = atoi(v);
     if (k >= 0 && k <= 1) m->tc_variant = k;
@@ -725,45 +723,58 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   // One persistent launch for all gated layers of the flow (k_flow_tc). The per-layer launches below remain for
   // per-launch profiling (mode 1), the layer tap of the parity tests, the phase trace and A/B runs (PWV_TC_FLOW=0).
   const bool tap_layer = taps && taps->layer_out && taps->layer_flow == flow;
+  // Launch form of the flow's gated layers, by job size (measured: profiles/r1_experiments_after_flow_kernel.txt,
+  // tools/sweep_modes.py). One persistent k_flow_tc launch for the whole flow saves the per-layer exit -> launch ->
+  // prologue -> refill (~5 us of a 41 us layer at c2), but its steady-state tile is 7-10 % slower than k_layer_tc's (more
+  // loop state under the 96-register cap) and a one-tile-per-CTA job pays a flag round trip per layer: it wins between
+  // ~2.5 and ~17 tiles per CTA per layer (2 .. 8 utterances of 1 s) and loses outside (c1: -13..-20 %, c3: -8 %).
+  // Outside the window: one k_layer_tc launch per layer, chained by programmatic dependent launch, no tile flags.
+  // PWV_TC_SEG = n forces k_flow_tc with n layers per launch (>= L: the whole flow).
+  const double tiles_per_cta = (double)tiles_body / (grid / 2);
+  const bool in_window = tiles_per_cta >= 2.5 && tiles_per_cta <= 17.0;
   const bool flow_kernel = m->use_flow && m->use_flags && m->tc_variant == 0 && m->profiling != 1 && !tap_layer && (!m->trace || getenv("PWV_TRACE_FLOW")) &&
-                           L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms;
+                           L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms && (m->tc_seg > 0 || in_window);
+  // tile flags between per-layer launches only pay in the same window (the A/B form PWV_TC_FLOW=0)
+  const bool layer_flags = m->use_flags && (in_window || m->tc_seg > 0);
   if (flow_kernel) {
-    pwv::TcFlowParams q;
-    q.act[0] = w.act[0]; q.act[1] = w.act[1];
-    q.images = m->tc.d_images + layer_base * pwv::TC_IMAGE_BYTES;
-    q.cbias = w.cbias;
-    q.flags = w.flags + (layer_base / 2) * 2 * (size_t)tiles_body;
-    q.N = N; q.T = T; q.t_mel = t_mel; q.hop = c_hop; q.L = L; q.cur0 = cur; q.tiles_per_utt = tiles_per_utt;
-    q.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
-    for (int j = 0; j < L; ++j) q.dilation[j] = hp.dilations[flow][j];
-    q.stagger = m->tc_stagger;
-    q.rotate = m->tc_rotate ? 1 : 0;
-    q.debug_unsafe = getenv("PWV_TC_DEBUG_UNSAFE") ? atoi(getenv("PWV_TC_DEBUG_UNSAFE")) : 0;   // timing experiments only
-    q.e1_lock = (m->tc_quiet && getenv("PWV_TC_E1LOCK") && atoi(getenv("PWV_TC_E1LOCK"))) ? 1 : 0;
-    q.trace = m->trace; q.trace_layer = m->trace ? m->trace_launch - (int)(layer_base / 2) : -1;
-    if (m->profiling == 2) PWV_PROF_MARK(m, st);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(pwv::TCF_THREADS);
-    cfg.dynamicSmemBytes = pwv::TCF_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = m->use_pdl ? 1 : 0;
-    if (m->tc_quiet && m->tc_hoist) {
-      if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true, true>, maps[0], maps[1], q));
-      else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true, true>, maps[0], maps[1], q));
-    } else if (m->tc_quiet) {
-      if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true>, maps[0], maps[1], q));
-      else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true>, maps[0], maps[1], q));
-    } else if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false>, maps[0], maps[1], q));
-    else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true>, maps[0], maps[1], q));
-    if (m->profiling == 2) PWV_PROF_MARK(m, st);
+    // layers per launch: the whole flow unless PWV_TC_SEG says otherwise (A/B runs, tests)
+    int seg = m->tc_seg > 0 ? m->tc_seg : L;
+    if (seg > L) seg = L;
+    for (int l0 = 0; l0 < L; l0 += seg) {
+      const int Ls = (L - l0 < seg) ? L - l0 : seg;
+      pwv::TcFlowParams q;
+      q.act[0] = w.act[0]; q.act[1] = w.act[1];
+      q.images = m->tc.d_images + layer_base * pwv::TC_IMAGE_BYTES;
+      q.cbias = w.cbias;
+      q.flags = w.flags + (layer_base / 2) * 2 * (size_t)tiles_body;
+      q.N = N; q.T = T; q.t_mel = t_mel; q.hop = c_hop; q.cur0 = cur; q.tiles_per_utt = tiles_per_utt;
+      q.L_total = L; q.l0 = l0; q.L = Ls; q.final_layer = (l0 + Ls == L) ? 1 : 0;
+      q.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+      for (int j = 0; j < L; ++j) q.dilation[j] = hp.dilations[flow][j];
+      q.stagger = m->tc_stagger;
+      q.rotate = m->tc_rotate ? 1 : 0;
+      q.trace = m->trace; q.trace_layer = m->trace ? m->trace_launch - (int)(layer_base / 2) : -1;
+      if (m->profiling == 2 && l0 == 0) PWV_PROF_MARK(m, st);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(pwv::tcf_threads(m->tc_quiet));
+      cfg.dynamicSmemBytes = pwv::TCF_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = m->use_pdl ? 1 : 0;
+      if (m->tc_quiet) {
+        if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true>, maps[0], maps[1], q));
+        else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true>, maps[0], maps[1], q));
+      } else if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false>, maps[0], maps[1], q));
+      else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true>, maps[0], maps[1], q));
+      if (m->profiling == 2 && l0 + Ls == L) PWV_PROF_MARK(m, st);
+      ++*launches;
+      cur ^= (Ls & 1);
+    }
     if (m->profiling) m->prof_launches += L;
-    ++*launches;
-    cur ^= (L & 1);
   }
   for (int j = 0; j < L && !flow_kernel; ++j) {
     pwv::TcLayerParams p;
@@ -779,8 +790,8 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       // tile handshake with the previous gated layer of the flow (see TcLayerParams); the first layer of a flow
       // follows k_front and waits for it as a whole. PWV_NO_TILE_FLAGS=1 restores whole-kernel waits everywhere.
       int* fl = w.flags + (layer_base / 2 + (size_t)j) * 2 * tiles_body;
-      p.flags_out = (m->use_flags && j + 1 < L) ? fl : nullptr;
-      p.flags_in = (m->use_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
+      p.flags_out = (layer_flags && j + 1 < L) ? fl : nullptr;
+      p.flags_in = (layer_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
       p.prev_dilation = j > 0 ? hp.dilations[flow][j - 1] : 0;
     }
     p.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;

@@ -834,19 +834,21 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_flow_tc: ALL gated layers of one flow (both bodies) in one persistent launch.
+// k_flow_tc: a RUN of consecutive gated layers of one flow (both bodies) in one persistent launch --
+// the whole flow, or any segment of it down to a single layer (TcFlowParams::l0 / L).
 //
-// Same tile pipeline as k_layer_tc (tile slots, TMEM layout, staging, warp roles, arithmetic -- the
-// results are bit-identical), with the layer loop inside the kernel and NO grid-wide synchronisation
-// between layers: a tile of layer l+1 starts as soon as the few tiles of layer l it depends on have been
-// published (per-tile flags, see k_layer_tc's tile handshake), whichever CTAs produced them. Measured
-// reason (c2, profiles/r1_tc_trace_v14_layer2.txt): of the 83k cycles a layer takes as a kernel of its own
-// only 63k are the steady-state pipeline; the rest is CTA exit -> launch -> prologue (barriers, TMEM,
-// 80 KB of weights) -> first loads, and the half-phase stagger of the two slots at both ends.
-// Here a CTA keeps walking its tile list layer after layer and the stagger survives the layer change.
+// Same tile pipeline as k_layer_tc (tile slots, TMEM layout, staging, arithmetic -- the results are
+// bit-identical), with the layer loop inside the kernel and NO grid-wide synchronisation between the
+// layers of a launch: a tile of layer l+1 starts as soon as the few tiles of layer l it depends on have
+// been published (per-tile flags, see k_layer_tc's tile handshake), whichever CTAs produced them.
+// Measured reason (c2, profiles/r1_tc_trace_v14_layer2.txt): of the 83k cycles a layer takes as a
+// kernel of its own only 63k are the steady-state pipeline; the rest is CTA exit -> launch -> prologue
+// (barriers, TMEM, 80 KB of weights) -> first loads, and the half-phase stagger of the two slots at both
+// ends. Here a CTA keeps walking its tile list layer after layer and the stagger survives the layer
+// change. The first layer of a launch waits for the previous kernel as a whole (griddepcontrol.wait).
 //
 // Weights are single-buffered (80 KB; two layers do not fit next to 128 KB of staging). They are
-// replaced in two parts by slot 0's MMA issuer: W1 (64 KB) + the bias/scale tail as soon as BOTH slots'
+// replaced in two parts by slot 0's helper: W1 (64 KB) + the bias/scale tail as soon as BOTH slots'
 // last GEMM1 of the layer has completed (tcgen05.commit on w1_free), W2 (16 KB) after both slots' last
 // GEMM2 -- by the time a slot's first tile of the next layer has been converted (1k cycles) W1 is
 // there. The 512-byte tail (dense bias, epilogue scales) is double-buffered by layer parity because the
@@ -854,8 +856,29 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
 //
 // Deadlock freedom: grid <= #SMs with one CTA per SM, so all CTAs are resident; every wait points at an
 // earlier (layer, tile) of some CTA or at this CTA's own other roles, never forward.
+//
+// Two forms (template flag QUIET):
+//   false  640 threads: 16 worker warps + per slot an MMA-issuer warp and a TMA-producer warp; every hand-off is
+//          an mbarrier that the waiting warps poll (the form of k_layer_tc).
+//   true   512 threads: the 16 worker warps only. The first warp of a slot (its "head" warp) also does the slot's
+//          helper work with one thread, at the points where the slot's workers would be waiting anyway -- a slot's
+//          events are strictly sequential (operands converted -> GEMM1 -> gate -> GEMM2 -> output copied out):
+//          it issues the slot's MMAs and TMA loads, loads the weights (slot 0) and publishes the tiles. Warp-to-warp
+//          hand-offs are hardware named barriers (the 7 other warps bar.arrive, the head warp bar.sync; nobody
+//          polls); only completions of the async units (TMA bytes landed, tcgen05.commit) are mbarriers; the commit
+//          barriers have ONE polling thread (the head warp's), which then joins the slot's bar.sync.
+//          Measured reasons: (1) ncu source counters of the polled form (profiles/r1_flow_kernel.txt): 40 % of
+//          all executed warp instructions were try_wait / branch / yield of polling warps (2,200 polls per tile);
+//          (2) ptxas wants 122-128 registers for these kernels and gets 96 at 640 threads (the register file is
+//          allocated per 128 threads: 544..640 threads all cap at 96); 512 threads lift the cap to 128
+//          (profiles/r1_experiments_after_flow_kernel.txt).
+//          Off the critical path by construction: the next tile's flags are LOADED before the GEMM1 issue loop and
+//          examined after it; a tile's publication (gpu-scope release fence) is deferred to the next tile's GEMM1
+//          window unless the head thread is about to block on other CTAs' tiles.
 // ------------------------------------------------------------------------------------------------
-constexpr int TCF_THREADS = TC_THREADS;                    // (a 21st warp would cap the kernel at 80 registers: 672 -> 768 threads' worth)
+constexpr int TCF_THREADS = TC_THREADS;                    // polled form (a 21st warp would cap the kernel at 80 registers)
+constexpr int TCF_THREADS_QUIET = TC_WORKER_WARPS * 32;
+constexpr int tcf_threads(bool quiet) { return quiet ? TCF_THREADS_QUIET : TCF_THREADS; }
 constexpr int TCF_MAIN_BYTES = TC_OFF_BD;                  // W1hi | W1lo | W2hi | W2lo
 constexpr int TCF_TAIL_BYTES = 512;                        // dense bias (256 B) + scales (256 B)
 constexpr int TCF_SMEM_TAIL0 = TC_SMEM_CB0 + 2 * TC_CB_BYTES;
@@ -864,18 +887,19 @@ constexpr int TCF_SMEM_BYTES = TCF_SMEM_BARS + 512;
 constexpr int TCF_MAX_LAYERS = 64;
 
 struct TcFlowParams {
-  float* act[2];            // ping/pong [2][N][T][64]; layer l reads act[(cur0 + l) & 1] through map[(cur0 + l) & 1], writes the other
-  const uint8_t* images;    // image of (flow, body 0, layer 0); (body b, layer l) at + (b * L + l) * TC_IMAGE_BYTES
-  const float* cbias;       // [2][L][N][t_mel][128] (pre-scaled, as for k_layer_tc)
-  int* flags;               // [L][2][N * tiles_per_utt], zeroed before the launch
-  int N, T, t_mel, hop, L, cur0, tiles_per_utt, cb_in_smem;
-  int dilation[TCF_MAX_LAYERS];
-  long long* trace;         // debug timeline of CTA 0 for layer trace_layer (or nullptr)
+  float* act[2];            // ping/pong [2][N][T][64]; layer l of the launch reads act[(cur0 + l) & 1] through map[(cur0 + l) & 1], writes the other
+  const uint8_t* images;    // image of (flow, body 0, layer 0); (body b, flow layer g) at + (b * L_total + g) * TC_IMAGE_BYTES
+  const float* cbias;       // [2][L_total][N][t_mel][128] (pre-scaled, as for k_layer_tc)
+  int* flags;               // [L_total][2][N * tiles_per_utt], zeroed before the forward
+  int N, T, t_mel, hop, cur0, tiles_per_utt, cb_in_smem;
+  int L_total;              // gated layers of the flow
+  int l0, L;                // this launch runs the flow's layers l0 .. l0 + L - 1
+  int final_layer;          // 1: layer l0 + L - 1 is the flow's last gated layer (its output is z, no dense GEMM)
+  int dilation[TCF_MAX_LAYERS];   // of the flow's layers
+  long long* trace;         // debug timeline of CTA 0 for flow layer trace_layer (or nullptr)
   int trace_layer;
   int stagger;              // see the producers
   int rotate;               // 1: rotate the tile-to-CTA assignment from layer to layer (see cta_of in the kernel)
-  int e1_lock;              // 1 (QUIET only, A/B): the two slots' gate phases (epilogue 1, MUFU-heavy) never overlap
-  int debug_unsafe;         // TIMING EXPERIMENTS ONLY, results undefined: 1 = flags without the gpu-scope fences, 2 = no flags at all
 };
 
 struct TcFlowBarriers {
@@ -883,36 +907,20 @@ struct TcFlowBarriers {
   uint64_t x_full[2], y_full[2], c_full[2], x_free[2], y_free[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2];
   uint32_t tmem_base;
   int mma_lock;
-  int e1_lock;
 };
 
 #define TCF_TRACE(role, l, j, k)                                                                    \
   do {                                                                                              \
-    if (p.trace && blockIdx.x == 0 && (l) == p.trace_layer && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
+    if (p.trace && blockIdx.x == 0 && p.l0 + (l) == p.trace_layer && (j) < 16) p.trace[((role) * 16 + (j)) * 16 + (k)] = clock64(); \
   } while (0)
 
-// QUIET hand-offs (template flag): the role-to-role hand-offs inside a tile slot go through hardware named
-// barriers instead of mbarriers that the waiting warps poll. Measured reason (ncu source counters of the polling
-// version, profiles/r1_flow_kernel.txt): 40 % of all executed warp instructions were try_wait / branch / yield
-// of polling warps (2,200 polls per tile), issued on the same four schedulers as the epilogue arithmetic.
-//   workers -> MMA issuer  (operands converted, z written):   workers bar.arrive, the issuer warp bar.sync
-//   MMA issuer -> workers  (accumulator complete):            the issuer's elected thread is the ONLY poller of the
-//                                                             tcgen05.commit mbarrier, then its warp bar.arrive,
-//                                                             the workers bar.sync (blocked, not polling)
-//   workers -> producer    (x[t-d] boxes converted, output copied out): workers bar.arrive, producer warp bar.sync
-// Only completions of the async units (TMA bytes landed, tcgen05.commit) still need mbarriers. A named barrier
-// is reused tile after tile: every arrival of tile j+1 is causally after the completion of tile j's barrier.
-constexpr int TCF_NB_AREADY = 1, TCF_NB_ZREADY = 3, TCF_NB_D1 = 5, TCF_NB_D2 = 7, TCF_NB_XFREE = 9, TCF_NB_YFREE = 11;   // + slot
-constexpr int TCF_NB_COUNT = 256 + 32;         // the slot's 8 worker warps + the one issuer / producer warp
+// named barriers of the QUIET form (+ slot): a barrier is reused tile after tile -- every arrival of tile j+1 is
+// causally after the completion of tile j's barrier
+constexpr int TCF_NB_AREADY = 1, TCF_NB_ZREADY = 3, TCF_NB_D1 = 5, TCF_NB_D2 = 7, TCF_NB_YFREE = 9;
+constexpr int TCF_NB_COUNT = 256;              // the slot's 8 worker warps
 
-// HOIST (template flag, needs nothing else): the same per-element arithmetic with the loads moved off the chain.
-// The phase traces show the gate phase at 2x its MUFU bound even when the other slot is idle (mutual-exclusion
-// experiment, profiles/r1_ab_e1lock.txt): each 16-channel round trip starts with a tcgen05.ld (~230 cycles) and
-// the conditioning-row loads, all exposed. Here epilogue 1 walks four 8-channel chunks with the next chunk's
-// accumulators in flight during the current chunk's arithmetic, chunk 0's conditioning rows are read before
-// the wait for GEMM1, and epilogue 2 reads its x[t] row before the wait for GEMM2.
-template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false, bool HOIST = false>
-__global__ void __launch_bounds__(TCF_THREADS, 1)
+template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false>
+__global__ void __launch_bounds__(tcf_threads(QUIET), 1)
 k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const __grid_constant__ TcFlowParams p) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -931,15 +939,145 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
   // the flow every CTA walks the same number of tiles (+-1). The per-tile flags make any assignment correct.
   // Only when every CTA keeps >= 1 tile per slot in every layer (the weight hand-over counts on both slots).
   const int rot = (p.rotate && tiles_body >= 2 * ctas_per_body) ? tiles_body % ctas_per_body : 0;
-  auto cta_of = [&](int l) { return rot ? (cta_in_body + l * rot) % ctas_per_body : cta_in_body; };
-  auto tiles_in = [&](int l, int s) {            // tiles of slot s of this CTA in layer l
+  auto cta_of = [&](int l) { return rot ? (cta_in_body + (p.l0 + l) * rot) % ctas_per_body : cta_in_body; };
+  auto tiles_in = [&](int l, int s) {            // tiles of slot s of this CTA in layer l (of the launch)
     const int c = cta_of(l);
     const int nl = (tiles_body > c) ? (tiles_body - c + ctas_per_body - 1) / ctas_per_body : 0;
     return (nl + 1 - s) / 2;
   };
+  auto is_last = [&](int l) { return p.final_layer && l == L - 1; };
 
+  // ---- TMA side of a slot (one elected thread of its producer / helper warp)
+  auto coords = [&](int s, int l, int j, int& n, int& t0) {
+    const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
+    n = tile / p.tiles_per_utt;
+    t0 = (tile % p.tiles_per_utt) * TC_TM;
+  };
+  auto map_of = [&](int l) { return ((p.cur0 + l) & 1) ? &map1 : &map0; };
+  auto issue_x = [&](int s, int l, int j) {
+    uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+    int n, t0;
+    coords(s, l, j, n, t0);
+    const int d = p.dilation[p.l0 + l];
+    mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
+    tma_load_3d(st, map_of(l), 0, t0 - d, body * p.N + n, &bars->x_full[s]);
+    tma_load_3d(st + TC_BOX_BYTES, map_of(l), 32, t0 - d, body * p.N + n, &bars->x_full[s]);
+  };
+  auto issue_y = [&](int s, int l, int j) {     // x[t] boxes + the conditioning rows of the frames the tile touches
+    uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+    int n, t0;
+    coords(s, l, j, n, t0);
+    mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
+    tma_load_3d(st + 2 * TC_BOX_BYTES, map_of(l), 0, t0, body * p.N + n, &bars->y_full[s]);
+    tma_load_3d(st + 3 * TC_BOX_BYTES, map_of(l), 32, t0, body * p.N + n, &bars->y_full[s]);
+    if (p.cb_in_smem) {
+      const float* cbias = p.cbias + ((size_t)body * p.L_total + p.l0 + l) * p.N * p.t_mel * 128;
+      const int f0 = (t0 + p.hop / 2) / p.hop, f1 = (min(t0 + TC_TM - 1, p.T - 1) + p.hop / 2) / p.hop;
+      const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * 512;
+      mbar_arrive_expect_tx(&bars->c_full[s], bytes);
+      bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
+    }
+  };
+  // the tiles of layer l-1 that tile j of layer l reads or whose reads it overwrites (see k_layer_tc): published?
+  // (layer 0 of the launch follows a kernel boundary: everything before it is complete)
+  struct Probe { int a, b, c, d, e; };
+  auto probe_load = [&](int s, int l, int j) -> Probe {      // relaxed loads of the (up to) five flags
+    Probe f = {1, 1, 1, 1, 1};
+    if (l == 0) return f;
+    int n, t0;
+    coords(s, l, j, n, t0);
+    const int d = p.dilation[p.l0 + l], dp = p.dilation[p.l0 + l - 1];
+    const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
+    const int* fl = p.flags + ((size_t)(p.l0 + l - 1) * 2 + body) * tiles_body + (size_t)n * p.tiles_per_utt;
+    const int hi = t0 + TC_TM - 1 - d, lo = max(t0 - d, 0);
+    const int k1 = hi >= 0 ? lo / TC_TM : k, k2 = hi >= 0 ? hi / TC_TM : k;
+    const int k3 = min(k + dp / TC_TM, last), k4 = min(k + (dp + TC_TM - 1) / TC_TM, last);
+    f.a = ld_relaxed_gpu(fl + k); f.b = ld_relaxed_gpu(fl + k1); f.c = ld_relaxed_gpu(fl + k2);
+    f.d = ld_relaxed_gpu(fl + k3); f.e = ld_relaxed_gpu(fl + k4);
+    return f;
+  };
+  auto probe_test = [&](int l, const Probe& f) -> bool {
+    if (l == 0) return true;
+    if (!(f.a & f.b & f.c & f.d & f.e)) return false;
+    fence_acq_rel_gpu();            // (acquire: the published tiles' rows are visible ...)
+    fence_proxy_async_global();     // (... to the TMA loads issued next)
+    return true;
+  };
+  auto tiles_ready = [&](int s, int l, int j) -> bool { return probe_test(l, probe_load(s, l, j)); };
+  auto publish = [&](int s, int l, int j) {   // after the slot's 256 workers have stored the tile's output (observed through a barrier)
+    const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
+    fence_acq_rel_gpu();               // (release, cumulative over the workers' stores)
+    st_relaxed_gpu(p.flags + ((size_t)(p.l0 + l) * 2 + body) * tiles_body + tile, 1);
+  };
+  // ---- tensor-core side of a slot (one elected thread of its issuer / helper warp)
+  const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
+  const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
+  constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
+  auto load_w1 = [&](int l) {     // W1 + bias/scale tail of layer l, once BOTH slots' last GEMM1 of layer l-1 has completed
+    const uint8_t* img = p.images + ((size_t)body * p.L_total + p.l0 + l) * TC_IMAGE_BYTES;
+    if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
+    mbar_arrive_expect_tx(&bars->w1_ready, 2 * TC_W1_BYTES + TCF_TAIL_BYTES);
+    for (int off = 0; off < 2 * TC_W1_BYTES; off += 16384) bulk_g2s(smem + off, img + off, 16384, &bars->w1_ready);
+    bulk_g2s(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES, img + TC_OFF_BD, TCF_TAIL_BYTES, &bars->w1_ready);
+  };
+  auto load_w2 = [&](int l) {     // W2 of layer l, once both slots' last GEMM2 of layer l-1 has completed
+    const uint8_t* img = p.images + ((size_t)body * p.L_total + p.l0 + l) * TC_IMAGE_BYTES;
+    if (l > 0) mbar_wait(&bars->w2_free, (l - 1) & 1);
+    mbar_arrive_expect_tx(&bars->w2_ready, 2 * TC_W2_BYTES);
+    bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
+  };
+  auto idle_layer = [&](int l) {  // a slot without tiles only keeps the weight hand-over going: one arrival per barrier phase
+    mbar_wait(&bars->w1_ready, l & 1);
+    mbar_arrive(&bars->w1_free);
+    if (!is_last(l)) {
+      mbar_wait(&bars->w2_ready, l & 1);
+      mbar_arrive(&bars->w2_free);
+    }
+  };
+  auto gemm1 = [&](int s, bool last_tile) {
+    const uint32_t tD = bars->tmem_base + s * 256, tAhi = tD + 128, tAlo = tD + 192;
+    tc_lock<SPLIT>(&bars->mma_lock);
+    tc_fence_after_sync();
+    uint32_t acc = 0;
+    if (SPLIT) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks, acc = 1)
+        mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks, acc = 1)
+      mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
+    mma_commit(&bars->d1_ready[s]);
+    if (last_tile) mma_commit(&bars->w1_free);     // this slot is done with W1 of the layer
+    tc_unlock<SPLIT>(&bars->mma_lock);
+  };
+  auto gemm2 = [&](int s, bool last_tile) {
+    const uint32_t tD = bars->tmem_base + s * 256, tAhi = tD + 128, tAlo = tD + 192;
+    tc_lock<SPLIT>(&bars->mma_lock);
+    tc_fence_after_sync();
+    uint32_t acc = 0;
+    if (SPLIT) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks, acc = 1)
+        mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks, acc = 1)
+      mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
+    mma_commit(&bars->d2_ready[s]);
+    if (last_tile) mma_commit(&bars->w2_free);
+    tc_unlock<SPLIT>(&bars->mma_lock);
+  };
+
+  constexpr int SETUP_WARP = QUIET ? 0 : TC_MMA_WARP;
   pdl_launch_dependents();
-  if (warp == TC_MMA_WARP) {
+  if (warp == SETUP_WARP) {
     if (lane == 0) {
       mbar_init(&bars->w1_ready, 1);
       mbar_init(&bars->w2_ready, 1);
@@ -957,7 +1095,6 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         mbar_init(&bars->d2_ready[s], 1);
       }
       bars->mma_lock = 0;
-      bars->e1_lock = 0;
       fence_mbar_init();
     }
     __syncwarp();
@@ -968,325 +1105,80 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (QUIET && (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1)) {
-    // ======================= MMA issuers, QUIET hand-offs: the whole warp walks the tile list (named barriers are
-    // warp-wide), the elected thread issues, loads the weights and polls the tcgen05.commit barriers =======================
-    const int s = warp - TC_MMA_WARP;
-    const bool leader = elect_one();
-    const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
-    const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
-    constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
-    const uint32_t tD = tmem + s * 256;
-    const uint32_t tAhi = tD + 128, tAlo = tD + 192;
-    uint32_t it = 0;
-    for (int l = 0; l < L && n_local > 0; ++l) {
-      const bool last_layer = l == L - 1;
-      const int tiles_s = tiles_in(l, s);
-      const uint8_t* img = p.images + ((size_t)body * L + l) * TC_IMAGE_BYTES;
-      if (leader) {
-        if (s == 0) {
-          if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
-          mbar_arrive_expect_tx(&bars->w1_ready, 2 * TC_W1_BYTES + TCF_TAIL_BYTES);
-          for (int off = 0; off < 2 * TC_W1_BYTES; off += 16384) bulk_g2s(smem + off, img + off, 16384, &bars->w1_ready);
-          bulk_g2s(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES, img + TC_OFF_BD, TCF_TAIL_BYTES, &bars->w1_ready);
-        }
-        if (tiles_s == 0) {
-          mbar_wait(&bars->w1_ready, l & 1);
-          mbar_arrive(&bars->w1_free);
-          if (!last_layer) {
-            mbar_wait(&bars->w2_ready, l & 1);
-            mbar_arrive(&bars->w2_free);
-          }
-        }
-      }
-      __syncwarp();
-      for (int j = 0; j < tiles_s; ++j, ++it) {
-        named_bar_sync(TCF_NB_AREADY + s, TCF_NB_COUNT);           // the slot's A1 operands are in TMEM
-        if (leader) {
-          if (j == 0) mbar_wait(&bars->w1_ready, l & 1);
-          tc_lock<SPLIT>(&bars->mma_lock);
-          tc_fence_after_sync();
-          TCF_TRACE(2, l, j, s * 8 + 0);
-          uint32_t acc = 0;
-          if (SPLIT) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks, acc = 1)
-              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks, acc = 1)
-            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-          mma_commit(&bars->d1_ready[s]);
-          if (j == tiles_s - 1) mma_commit(&bars->w1_free);
-          tc_unlock<SPLIT>(&bars->mma_lock);
-          TCF_TRACE(2, l, j, s * 8 + 1);
-          if (!last_layer && s == 0 && j == 0) {
-            if (l > 0) mbar_wait(&bars->w2_free, (l - 1) & 1);
-            mbar_arrive_expect_tx(&bars->w2_ready, 2 * TC_W2_BYTES);
-            bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
-          }
-          mbar_wait(&bars->d1_ready[s], it & 1);                   // GEMM1 complete ...
-          if (p.e1_lock && !last_layer) tc_lock<true>(&bars->e1_lock);    // (... and the other slot is out of its gate phase)
-        }
-        __syncwarp();
-        named_bar_arrive(TCF_NB_D1 + s, TCF_NB_COUNT);             // ... relayed to the slot's workers
-        if (last_layer) continue;
-        named_bar_sync(TCF_NB_ZREADY + s, TCF_NB_COUNT);           // z is in TMEM
-        if (leader) {
-          if (p.e1_lock) tc_unlock<true>(&bars->e1_lock);
-          if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
-          tc_lock<SPLIT>(&bars->mma_lock);
-          tc_fence_after_sync();
-          TCF_TRACE(2, l, j, s * 8 + 2);
-          uint32_t acc = 0;
-          if (SPLIT) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks, acc = 1)
-              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks, acc = 1)
-            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-          mma_commit(&bars->d2_ready[s]);
-          if (j == tiles_s - 1) mma_commit(&bars->w2_free);
-          tc_unlock<SPLIT>(&bars->mma_lock);
-          TCF_TRACE(2, l, j, s * 8 + 3);
-          mbar_wait(&bars->d2_ready[s], it & 1);
-        }
-        __syncwarp();
-        named_bar_arrive(TCF_NB_D2 + s, TCF_NB_COUNT);
-      }
-    }
-  } else if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
-    // ======================= MMA issuers (one per tile slot); slot 0's also hands the weights over =======================
+  if (!QUIET && (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1)) {
+    // ======================= MMA issuers (one per tile slot), polled form; slot 0's also hands the weights over =======================
     if (elect_one() && n_local > 0) {
       const int s = warp - TC_MMA_WARP;
-      const uint32_t w1hi = smem_u32(smem + TC_OFF_W1HI), w1lo = smem_u32(smem + TC_OFF_W1LO);
-      const uint32_t w2hi = smem_u32(smem + TC_OFF_W2HI), w2lo = smem_u32(smem + TC_OFF_W2LO);
-      constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
-      const uint32_t tD = tmem + s * 256;
-      const uint32_t tAhi = tD + 128, tAlo = tD + 192;
       uint32_t it = 0;                                  // tiles of this slot so far (barrier phase)
       for (int l = 0; l < L; ++l) {
-        const bool last_layer = l == L - 1;
+        const bool last_layer = is_last(l);
         const int tiles_s = tiles_in(l, s);
-        const uint8_t* img = p.images + ((size_t)body * L + l) * TC_IMAGE_BYTES;
-        if (s == 0) {       // W1 + bias/scale tail of layer l, once BOTH slots' last GEMM1 of layer l-1 has completed
-          if (l > 0) mbar_wait(&bars->w1_free, (l - 1) & 1);
-          mbar_arrive_expect_tx(&bars->w1_ready, 2 * TC_W1_BYTES + TCF_TAIL_BYTES);
-          for (int off = 0; off < 2 * TC_W1_BYTES; off += 16384) bulk_g2s(smem + off, img + off, 16384, &bars->w1_ready);
-          bulk_g2s(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES, img + TC_OFF_BD, TCF_TAIL_BYTES, &bars->w1_ready);
-        }
-        if (tiles_s == 0) {                             // (one tile in the CTA: slot 1 only keeps the weight hand-over going,
-          mbar_wait(&bars->w1_ready, l & 1);            //  in step with the layers: one arrival per barrier phase)
-          mbar_arrive(&bars->w1_free);
-          if (!last_layer) {
-            mbar_wait(&bars->w2_ready, l & 1);
-            mbar_arrive(&bars->w2_free);
-          }
+        if (s == 0) load_w1(l);
+        if (tiles_s == 0) {
+          idle_layer(l);
           continue;
         }
         for (int j = 0; j < tiles_s; ++j, ++it) {
           mbar_wait(&bars->a_ready[s], it & 1);
           if (j == 0) mbar_wait(&bars->w1_ready, l & 1);
-          tc_lock<SPLIT>(&bars->mma_lock);
-          tc_fence_after_sync();
           TCF_TRACE(2, l, j, s * 8 + 0);
-          uint32_t acc = 0;
-          if (SPLIT) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks, acc = 1)
-              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1lo + ks * 2 * 2048, 2048, 128), ID1, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks, acc = 1)
-            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w1hi + ks * 2 * 2048, 2048, 128), ID1, acc);
-          mma_commit(&bars->d1_ready[s]);
-          if (j == tiles_s - 1) mma_commit(&bars->w1_free);     // this slot is done with W1 of layer l
-          tc_unlock<SPLIT>(&bars->mma_lock);
+          gemm1(s, j == tiles_s - 1);
           TCF_TRACE(2, l, j, s * 8 + 1);
           if (last_layer) continue;
-          if (s == 0 && j == 0) {     // W2 of layer l, once both slots' last GEMM2 of layer l-1 has completed
-            if (l > 0) mbar_wait(&bars->w2_free, (l - 1) & 1);
-            mbar_arrive_expect_tx(&bars->w2_ready, 2 * TC_W2_BYTES);
-            bulk_g2s(smem + TC_OFF_W2HI, img + TC_OFF_W2HI, 2 * TC_W2_BYTES, &bars->w2_ready);
-          }
+          if (s == 0 && j == 0) load_w2(l);
           mbar_wait(&bars->z_ready[s], it & 1);
           if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
-          tc_lock<SPLIT>(&bars->mma_lock);
-          tc_fence_after_sync();
           TCF_TRACE(2, l, j, s * 8 + 2);
-          acc = 0;
-          if (SPLIT) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks, acc = 1)
-              mma_f16_ts(tD, tAlo + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2lo + ks * 2 * 1024, 1024, 128), ID2, 1);
-          }
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks, acc = 1)
-            mma_f16_ts(tD, tAhi + ks * 8, smem_desc_kmajor_noswizzle(w2hi + ks * 2 * 1024, 1024, 128), ID2, acc);
-          mma_commit(&bars->d2_ready[s]);
-          if (j == tiles_s - 1) mma_commit(&bars->w2_free);
-          tc_unlock<SPLIT>(&bars->mma_lock);
+          gemm2(s, j == tiles_s - 1);
           TCF_TRACE(2, l, j, s * 8 + 3);
         }
       }
     }
     __syncwarp();
-  } else if (warp >= TC_TMA_WARP) {
-    // ======================= TMA producers (one per tile slot) =======================
-    // (QUIET: the whole warp walks the tile list because named barriers are warp-wide; `leader` does the work)
-    if (QUIET || elect_one()) {
+  } else if (!QUIET && warp >= TC_TMA_WARP) {
+    // ======================= TMA producers (one per tile slot), polled form =======================
+    if (elect_one()) {
       const int s = warp - TC_TMA_WARP;
-      const bool leader = QUIET ? elect_one() : true;
       tma_prefetch_desc(&map0);
       tma_prefetch_desc(&map1);
-      uint8_t* st = smem + TC_SMEM_STAGE0 + s * TC_STAGE_BYTES;
+      pdl_wait_prior_grid();      // the launch's input (k_front / the previous layers' kernel) is complete
+      // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0), when
+      // its first GEMM1 has completed (1) or when its first gate phase is through (2)
+      if (s == 1 && n_local > 0) {
+        if (p.stagger == 1) mbar_wait(&bars->d1_ready[0], 0);
+        else if (p.stagger == 2) mbar_wait(&bars->z_ready[0], 0);
+        else mbar_wait(&bars->y_full[0], 0);
+      }
       // this slot's tile list: layer after layer, tiles_in(l, s) tiles each (the same count in every layer unless
       // the assignment rotates; a slot without tiles in layer 0 has none at all)
-      auto coords = [&](int l, int j, int& n, int& t0) {
-        const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
-        n = tile / p.tiles_per_utt;
-        t0 = (tile % p.tiles_per_utt) * TC_TM;
-      };
-      auto map_of = [&](int l) { return ((p.cur0 + l) & 1) ? &map1 : &map0; };
-      auto issue_x = [&](int l, int j) {
-        int n, t0;
-        coords(l, j, n, t0);
-        const int d = p.dilation[l];
-        mbar_arrive_expect_tx(&bars->x_full[s], 2 * TC_BOX_BYTES);
-        tma_load_3d(st, map_of(l), 0, t0 - d, body * p.N + n, &bars->x_full[s]);
-        tma_load_3d(st + TC_BOX_BYTES, map_of(l), 32, t0 - d, body * p.N + n, &bars->x_full[s]);
-      };
-      auto issue_y = [&](int l, int j) {     // x[t] boxes + the conditioning rows of the frames the tile touches
-        int n, t0;
-        coords(l, j, n, t0);
-        mbar_arrive_expect_tx(&bars->y_full[s], 2 * TC_BOX_BYTES);
-        tma_load_3d(st + 2 * TC_BOX_BYTES, map_of(l), 0, t0, body * p.N + n, &bars->y_full[s]);
-        tma_load_3d(st + 3 * TC_BOX_BYTES, map_of(l), 32, t0, body * p.N + n, &bars->y_full[s]);
-        if (p.cb_in_smem) {
-          const float* cbias = p.cbias + ((size_t)body * L + l) * p.N * p.t_mel * 128;
-          const int f0 = (t0 + p.hop / 2) / p.hop, f1 = (min(t0 + TC_TM - 1, p.T - 1) + p.hop / 2) / p.hop;
-          const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * 512;
-          mbar_arrive_expect_tx(&bars->c_full[s], bytes);
-          bulk_g2s(smem + TC_SMEM_CB0 + s * TC_CB_BYTES, cbias + ((size_t)n * p.t_mel + f0) * 128, bytes, &bars->c_full[s]);
-        }
-      };
-      // the tiles of layer l-1 that tile j of layer l reads or whose reads it overwrites (see k_layer_tc): published?
-      auto tiles_ready = [&](int l, int j) -> bool {
-        if (l == 0 || p.debug_unsafe == 2) return true;
-        int n, t0;
-        coords(l, j, n, t0);
-        const int d = p.dilation[l], dp = p.dilation[l - 1];
-        const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
-        const int* f = p.flags + ((size_t)(l - 1) * 2 + body) * tiles_body + (size_t)n * p.tiles_per_utt;
-        const int hi = t0 + TC_TM - 1 - d, lo = max(t0 - d, 0);
-        const int k1 = hi >= 0 ? lo / TC_TM : k, k2 = hi >= 0 ? hi / TC_TM : k;
-        const int k3 = min(k + dp / TC_TM, last), k4 = min(k + (dp + TC_TM - 1) / TC_TM, last);
-        const int a = ld_relaxed_gpu(f + k), b = ld_relaxed_gpu(f + k1), c = ld_relaxed_gpu(f + k2);
-        const int d4 = ld_relaxed_gpu(f + k3), e = ld_relaxed_gpu(f + k4);
-        if (!(a & b & c & d4 & e)) return false;
-        if (p.debug_unsafe) return true;
-        fence_acq_rel_gpu();            // (acquire: the published tiles' rows are visible ...)
-        fence_proxy_async_global();     // (... to the TMA loads issued next)
-        return true;
-      };
-      auto publish = [&](int l, int j) {   // after y_free[s]: all 256 workers of the slot have stored the tile's output
-        const int tile = cta_of(l) + (s + 2 * j) * ctas_per_body;
-        if (p.debug_unsafe == 2) return;
-        if (!p.debug_unsafe)
-        fence_acq_rel_gpu();               // (release, cumulative over the workers' stores observed through y_free)
-        st_relaxed_gpu(p.flags + ((size_t)l * 2 + body) * tiles_body + tile, 1);
-      };
-      if (leader) {
-        pdl_wait_prior_grid();      // the flow's input (k_front) and everything before it is complete
-        // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0), when
-        // its first GEMM1 has completed (1) or when its first gate phase is through (2; an mbarrier only without QUIET)
-        if (s == 1 && n_local > 0) {
-          if (p.stagger == 1 || (QUIET && p.stagger == 2)) mbar_wait(&bars->d1_ready[0], 0);
-          else if (p.stagger == 2) mbar_wait(&bars->z_ready[0], 0);
-          else mbar_wait(&bars->y_full[0], 0);
-        }
-        if (tiles_in(0, s) > 0) {
-          issue_x(0, 0);
-          issue_y(0, 0);
-        }
-      }
       int l = 0, j = 0, tiles_l = tiles_in(0, s);       // the tile in flight and its layer's tile count
-      uint32_t q = 0;                                   // tiles of this slot so far (barrier phase)
-      if (QUIET) {
-        // Same protocol as below; the "boxes converted" / "output copied out" events are named barriers the
-        // slot's workers arrive on (also for the slot's very last tile, so that no arrival is left pending).
-        __syncwarp();
-        while (tiles_l > 0) {
-          const int ln = (j + 1 == tiles_l) ? l + 1 : l, jn = (j + 1 == tiles_l) ? 0 : j + 1;     // the slot's next tile
-          const bool more = ln < L;
-          named_bar_sync(TCF_NB_XFREE + s, TCF_NB_COUNT);
-          bool early = false;
-          if (leader && more) {
-            early = tiles_ready(ln, jn);
-            if (early) {
-              issue_x(ln, jn);
-              TCF_TRACE(3, l, j, s * 8 + 0);
-            }
-          }
-          __syncwarp();
-          named_bar_sync(TCF_NB_YFREE + s, TCF_NB_COUNT);
-          if (leader && more) {
-            if (early) {
-              issue_y(ln, jn);
-              if (l < L - 1) publish(l, j);
-            } else {
-              if (l < L - 1) publish(l, j);
-              while (!tiles_ready(ln, jn)) {
-              }
-              issue_x(ln, jn);
-              issue_y(ln, jn);
-            }
-            TCF_TRACE(3, l, j, s * 8 + 2);
-          }
-          __syncwarp();
-          if (!more) break;
-          if (ln != l) tiles_l = tiles_in(ln, s);
-          l = ln;
-          j = jn;
-        }
-      } else
+      if (tiles_l > 0) {
+        issue_x(s, 0, 0);
+        issue_y(s, 0, 0);
+      }
       // A tile is published as soon as it is stored, NEVER after a wait for other CTAs' tiles (two CTAs whose next
       // tiles need each other's current tiles would wait forever): the inputs of the slot's next tile are only
       // PROBED early (to prefetch its x[t-d] boxes, the normal case inside a layer); if they are not all there yet
       // the blocking wait comes after this tile's publication.
-      for (; tiles_l > 0; ++q) {
+      for (uint32_t q = 0; tiles_l > 0; ++q) {          // q: tiles of this slot so far (barrier phase)
         const int ln = (j + 1 == tiles_l) ? l + 1 : l, jn = (j + 1 == tiles_l) ? 0 : j + 1;       // the slot's next tile
-        if (ln == L) break;                             // (last layer: nothing to publish, nothing to refill)
+        if (ln == L) break;                             // (the launch's last tile: nothing to refill; published by the kernel's end)
         mbar_wait(&bars->x_free[s], q & 1);             // the slot's x[t-d] boxes have been converted
-        const bool early = tiles_ready(ln, jn);
+        const bool early = tiles_ready(s, ln, jn);
         if (early) {
-          issue_x(ln, jn);
+          issue_x(s, ln, jn);
           TCF_TRACE(3, l, j, s * 8 + 0);
         }
         mbar_wait(&bars->y_free[s], q & 1);             // output copied out of the x[t] boxes, conditioning rows read
         if (early) {
-          issue_y(ln, jn);
-          if (l < L - 1) publish(l, j);
+          issue_y(s, ln, jn);
+          if (l < L - 1) publish(s, l, j);
         } else {
-          if (l < L - 1) publish(l, j);
-          while (!tiles_ready(ln, jn)) {
+          if (l < L - 1) publish(s, l, j);
+          while (!tiles_ready(s, ln, jn)) {
           }
-          issue_x(ln, jn);
-          issue_y(ln, jn);
+          issue_x(s, ln, jn);
+          issue_y(s, ln, jn);
         }
         TCF_TRACE(3, l, j, s * 8 + 2);
         if (ln != l) tiles_l = tiles_in(ln, s);
@@ -1306,14 +1198,38 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
     uint8_t* my_x = stage + half * TC_BOX_BYTES + r * 128;
     uint8_t* my_y = stage + 2 * TC_BOX_BYTES + half * TC_BOX_BYTES + r * 128;
     const bool tracer = (warp & 7) == 0 && lane == 0;
+    // QUIET form: the slot's head warp (its first one) does the slot's helper work with its lane 0
+    const bool head_warp = QUIET && (warp & 7) == 0, head = head_warp && lane == 0;
+    int pub_l = -1, pub_j = 0;                          // head: tile whose publication is pending
+    if (head) {
+      tma_prefetch_desc(&map0);
+      tma_prefetch_desc(&map1);
+      pdl_wait_prior_grid();      // the launch's input (k_front / the previous layers' kernel) is complete
+      // half-phase stagger of the two slots: slot 1 starts loading when slot 0's first boxes have landed (0) or
+      // when its first GEMM1 has completed (1, 2)
+      if (slot == 1 && n_local > 0) {
+        if (p.stagger >= 1) mbar_wait(&bars->d1_ready[0], 0);
+        else mbar_wait(&bars->y_full[0], 0);
+      }
+      if (tiles_in(0, slot) > 0) {
+        issue_x(slot, 0, 0);
+        issue_y(slot, 0, 0);
+      }
+    }
+    if (QUIET) __syncwarp();
     uint32_t it = 0;
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
-      const bool last_layer = l == L - 1;
+      const bool last_layer = is_last(l);
       const int tiles_s = tiles_in(l, slot), cta_l = cta_of(l);
+      if (head && n_local > 0) {        // weights (both W1 barriers' previous phases are normally long complete here)
+        if (slot == 0) load_w1(l);
+        if (tiles_s == 0) idle_layer(l);
+      }
+      if (QUIET) __syncwarp();
       const float* tail = reinterpret_cast<const float*>(smem + TCF_SMEM_TAIL0 + (l & 1) * TCF_TAIL_BYTES);
       const float* bd_s = tail + half * 32;
-      const float* cbias_l = p.cbias + ((size_t)body * L + l) * p.N * p.t_mel * 128;
+      const float* cbias_l = p.cbias + ((size_t)body * p.L_total + p.l0 + l) * p.N * p.t_mel * 128;
       float* x_out = p.act[(p.cur0 + l + 1) & 1];
       float sf = 0.f, sg = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -1326,16 +1242,50 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         mbar_wait(&bars->x_full[slot], par);
         if (tracer) TCF_TRACE(slot, l, j, 1);
         tc_prep<BF16, SPLIT, PK>(my_x, r, tAhi + half * 16, tAlo + half * 16);
-        if (QUIET) named_bar_arrive(TCF_NB_XFREE + slot, TCF_NB_COUNT);
-        else mbar_arrive(&bars->x_free[slot]);
+        if (!QUIET) mbar_arrive(&bars->x_free[slot]);   // (QUIET: the helper refills these boxes after GEMM1, which implies this)
         if (tracer) TCF_TRACE(slot, l, j, 2);
         mbar_wait(&bars->y_full[slot], par);
         if (tracer) TCF_TRACE(slot, l, j, 3);
         tc_prep<BF16, SPLIT, PK>(my_y, r, tAhi + 32 + half * 16, tAlo + 32 + half * 16);
         tmem_wait_st();
         tc_fence_before_sync();
-        if (QUIET) named_bar_arrive(TCF_NB_AREADY + slot, TCF_NB_COUNT);
-        else mbar_arrive(&bars->a_ready[slot]);
+        // the slot's next tile (l, j) -> (ln, jn) (head only; a layer's tile count never drops to 0 once the slot has tiles)
+        const int ln = (j + 1 == tiles_s) ? l + 1 : l, jn = (j + 1 == tiles_s) ? 0 : j + 1;
+        const bool more = ln < L;
+        bool early = false;
+        if (!QUIET) {
+          mbar_arrive(&bars->a_ready[slot]);
+        } else if (!head_warp) {
+          named_bar_arrive(TCF_NB_AREADY + slot, TCF_NB_COUNT);
+        } else {
+          named_bar_sync(TCF_NB_AREADY + slot, TCF_NB_COUNT);      // the slot's A1 operands are in TMEM (x[t-d] boxes free)
+          if (head) {
+            if (j == 0) mbar_wait(&bars->w1_ready, l & 1);
+            // the next tile's flags: loaded now, examined after the MMA issue loop (which the tensor pipe throttles)
+            Probe pr = {1, 1, 1, 1, 1};
+            if (more) pr = probe_load(slot, ln, jn);
+            TCF_TRACE(2, l, j, slot * 8 + 0);
+            gemm1(slot, j == tiles_s - 1);
+            TCF_TRACE(2, l, j, slot * 8 + 1);
+            if (!last_layer && slot == 0 && j == 0) load_w2(l);
+            // prefetch the next tile's x[t-d] boxes if its inputs are published (only PROBED: a tile is published NEVER
+            // after a wait for other CTAs' tiles -- two CTAs whose next tiles need each other's current tiles would
+            // wait forever -- so the blocking wait comes after this tile's publication, below)
+            if (more) {
+              early = probe_test(ln, pr);
+              if (early) {
+                issue_x(slot, ln, jn);
+                TCF_TRACE(3, l, j, slot * 8 + 0);
+              }
+            }
+            if (pub_l >= 0) {                                      // the previous tile's deferred publication
+              publish(slot, pub_l, pub_j);
+              pub_l = -1;
+            }
+            mbar_wait(&bars->d1_ready[slot], par);                 // GEMM1 complete
+          }
+          __syncwarp();
+        }
         if (tracer) TCF_TRACE(slot, l, j, 4);
 
         if (j == 0) {                     // the layer's scales / dense bias arrive with W1
@@ -1352,83 +1302,55 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         }
 
         // ---- epilogue 1: z = tanh(f) * sigmoid(g) on my 32 channels
-        if (HOIST) {
-          if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);        // (landed with the x[t] boxes, long ago)
-          float4 cf[2] = {cb[0], cb[1]}, cg[2] = {cb[16], cb[17]};        // chunk 0's conditioning rows, before the wait
-          if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);
-          else mbar_wait(&bars->d1_ready[slot], par);
-          tc_fence_after_sync();
-          if (tracer) TCF_TRACE(slot, l, j, 5);
-          uint32_t fa[8], ga[8], fb[8], gb[8];
-          tmem_ld8(tD + half * 32, fa);
-          tmem_ld8(tD + 64 + half * 32, ga);
-          tmem_wait_ld();
-          if (tracer) TCF_TRACE(slot, l, j, 12);
+        if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);     // (the slot's issuer saw GEMM1's commit)
+        else mbar_wait(&bars->d1_ready[slot], par);
+        tc_fence_after_sync();
+        if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
+        if (tracer) TCF_TRACE(slot, l, j, 5);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {        // 8 channels per chunk; chunk c+1's accumulators load during chunk c's arithmetic
-            uint32_t (&fr)[8] = (c & 1) ? fb : fa, (&gr)[8] = (c & 1) ? gb : ga;
-            if (c < 3) {
-              tmem_ld8(tD + half * 32 + (c + 1) * 8, (c & 1) ? fa : fb);
-              tmem_ld8(tD + 64 + half * 32 + (c + 1) * 8, (c & 1) ? ga : gb);
-            }
-            float z[8];
-            tc_gate<BF16, PK, 8>(fr, gr, cf, cg, sf, sg, z);
-            if (c < 3) { cf[0] = cb[(c + 1) * 2]; cf[1] = cb[(c + 1) * 2 + 1]; cg[0] = cb[16 + (c + 1) * 2]; cg[1] = cb[16 + (c + 1) * 2 + 1]; }
-            if (last_layer) {
-              *box_chunk(my_y, r, c * 2) = make_float4(z[0], z[1], z[2], z[3]);
-              *box_chunk(my_y, r, c * 2 + 1) = make_float4(z[4], z[5], z[6], z[7]);
-            } else {
-              uint32_t hi[4], lo[4];
-              split8x<BF16, SPLIT, PK>(z, hi, lo);
-              tmem_st4(tAhi + half * 16 + c * 4, hi);
-              if (SPLIT) tmem_st4(tAlo + half * 16 + c * 4, lo);
-            }
-            if (c < 3) tmem_wait_ld();
-            if (c == 1 && tracer) TCF_TRACE(slot, l, j, 13);
-          }
-        } else {
-          if (QUIET) named_bar_sync(TCF_NB_D1 + slot, TCF_NB_COUNT);     // (the slot's issuer saw GEMM1's commit)
-          else mbar_wait(&bars->d1_ready[slot], par);
-          tc_fence_after_sync();
-          if (p.cb_in_smem) mbar_wait(&bars->c_full[slot], par);
-          if (tracer) TCF_TRACE(slot, l, j, 5);
-  #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t fr[16], gr[16];
-            tmem_ld16(tD + half * 32 + c * 16, fr);
-            tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
-            tmem_wait_ld();
-            if (tracer) TCF_TRACE(slot, l, j, 12 + c);
-            float z[16];
-            tc_gate<BF16, PK, 16>(fr, gr, cb + c * 4, cb + 16 + c * 4, sf, sg, z);
-            if (last_layer) {               // z itself is the output (x[t] is dead)
-  #pragma unroll
-              for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
-            } else {
-              uint32_t hi[8], lo[8];
-              float v0[8], v1[8];
-  #pragma unroll
-              for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
-              split8x<BF16, SPLIT, PK>(v0, hi, lo);
-              split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
-              tmem_st8(tAhi + half * 16 + c * 8, hi);
-              if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
-            }
+        for (int c = 0; c < 2; ++c) {
+          uint32_t fr[16], gr[16];
+          tmem_ld16(tD + half * 32 + c * 16, fr);
+          tmem_ld16(tD + 64 + half * 32 + c * 16, gr);
+          tmem_wait_ld();
+          if (tracer) TCF_TRACE(slot, l, j, 12 + c);
+          float z[16];
+          tc_gate<BF16, PK, 16>(fr, gr, cb + c * 4, cb + 16 + c * 4, sf, sg, z);
+          if (last_layer) {               // z itself is the output (x[t] is dead)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *box_chunk(my_y, r, c * 4 + q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+          } else {
+            uint32_t hi[8], lo[8];
+            float v0[8], v1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
+            split8x<BF16, SPLIT, PK>(v0, hi, lo);
+            split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
+            tmem_st8(tAhi + half * 16 + c * 8, hi);
+            if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
           }
         }
         if (!last_layer) {
           tmem_wait_st();
           tc_fence_before_sync();
-          if (QUIET) named_bar_arrive(TCF_NB_ZREADY + slot, TCF_NB_COUNT);
-          else mbar_arrive(&bars->z_ready[slot]);
+          if (!QUIET) {
+            mbar_arrive(&bars->z_ready[slot]);
+          } else if (!head_warp) {
+            named_bar_arrive(TCF_NB_ZREADY + slot, TCF_NB_COUNT);
+          } else {
+            named_bar_sync(TCF_NB_ZREADY + slot, TCF_NB_COUNT);    // z is in TMEM
+            if (head) {
+              if (j == 0) mbar_wait(&bars->w2_ready, l & 1);
+              TCF_TRACE(2, l, j, slot * 8 + 2);
+              gemm2(slot, j == tiles_s - 1);
+              TCF_TRACE(2, l, j, slot * 8 + 3);
+              mbar_wait(&bars->d2_ready[slot], par);
+            }
+            __syncwarp();
+          }
           if (tracer) TCF_TRACE(slot, l, j, 6);
 
           // ---- epilogue 2: out = x[t] + D2 + b_dense (in place in my staged x[t] half row)
-          float4 xrow[8];
-          if (HOIST) {                    // my x[t] half row, before the wait for GEMM2
-#pragma unroll
-            for (int q = 0; q < 8; ++q) xrow[q] = *box_chunk(my_y, r, q);
-          }
           if (QUIET) named_bar_sync(TCF_NB_D2 + slot, TCF_NB_COUNT);
           else mbar_wait(&bars->d2_ready[slot], par);
           tc_fence_after_sync();
@@ -1441,7 +1363,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(bd_s + q * 4);
-            const float4 xv = HOIST ? xrow[q] : *box_chunk(my_y, r, q);
+            const float4 xv = *box_chunk(my_y, r, q);
             const uint32_t* d = &dr[q >> 2][(q & 3) * 4];
             float4 o;
             if (PK) {
@@ -1474,15 +1396,35 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
         }
         if (tracer) TCF_TRACE(slot, l, j, 11);
         tc_fence_before_sync();
-        if (QUIET) named_bar_arrive(TCF_NB_YFREE + slot, TCF_NB_COUNT);
-        else mbar_arrive(&bars->y_free[slot]);
+        if (!QUIET) {
+          mbar_arrive(&bars->y_free[slot]);
+        } else if (!head_warp) {
+          named_bar_arrive(TCF_NB_YFREE + slot, TCF_NB_COUNT);
+        } else {
+          named_bar_sync(TCF_NB_YFREE + slot, TCF_NB_COUNT);       // output copied out of the x[t] boxes, conditioning rows read
+          if (head) {
+            if (more && early) issue_y(slot, ln, jn);
+            if (l < L - 1) {                  // a later layer of this launch reads the tile
+              if (more && !early) publish(slot, l, j);             // about to block on other CTAs' tiles: publish first
+              else { pub_l = l; pub_j = j; }                       // otherwise in the next tile's GEMM1 window
+            }
+            if (more && !early) {
+              while (!tiles_ready(slot, ln, jn)) {
+              }
+              issue_x(slot, ln, jn);
+              issue_y(slot, ln, jn);
+            }
+            TCF_TRACE(3, l, j, slot * 8 + 2);
+          }
+          __syncwarp();
+        }
         if (tracer) TCF_TRACE(slot, l, j, 8);
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == TC_MMA_WARP) tmem_dealloc(tmem, 512);
+  if (warp == SETUP_WARP) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------

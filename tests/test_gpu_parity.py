@@ -268,15 +268,18 @@ def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
-@pytest.mark.parametrize('quiet,rotate', [(0, 0), (1, 0), (1, 1)])
-def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision, quiet, rotate):
+@pytest.mark.parametrize('quiet,rotate,seg', [(0, 0, 100), (0, 1, 100), (0, 1, 1), (0, 0, 3), (0, 0, 0)])
+def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision, quiet, rotate, seg):
     """k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
     the same tile pipeline as the one-launch-per-layer path (PWV_TC_FLOW=0): outputs must be BIT-identical,
     including one-tile CTAs (idle second slot), single-layer flows (no GEMM2 at all), d >= T and ragged tiles.
-    Covered for both hand-off styles (PWV_TC_QUIET: polled mbarriers / named barriers) and with the per-layer
-    rotation of the tile-to-CTA assignment (PWV_TC_ROTATE)."""
+    Covered with and without the per-layer rotation of the tile-to-CTA assignment (PWV_TC_ROTATE) and for every
+    launch segmentation (PWV_TC_SEG layers per launch: the whole flow, one layer, three layers -- a ragged last
+    segment --, 0 = launch form chosen by job size, the default). The experimental 512-thread form (PWV_TC_QUIET=1)
+    is not part of the product path and is not exercised here (profiles/r1_experiments_after_flow_kernel.txt)."""
     monkeypatch.setenv('PWV_TC_QUIET', str(quiet))
     monkeypatch.setenv('PWV_TC_ROTATE', str(rotate))
+    monkeypatch.setenv('PWV_TC_SEG', str(seg))
     W = pkg('weights')
     cases = [(None, 2, 4000), (((1, 512, 2), (256, 1)), 5, 1040), (((1, 512, 2), (256, 1)), 1, 80), (((1,), (2, 4), (128,)), 3, 2000),
              (((1, 2, 4, 8, 16, 32, 64, 128, 256, 512) * 3,), 4, 8000), (None, 8, 16000)]

@@ -4,7 +4,7 @@
     compute-sanitizer --tool memcheck python tools/sanitize.py > profiles/..._memcheck.txt
 
 Graphs: a 2-flow graph with a d >= T tap and a ragged last tile ('repeat' conditioning, all three precisions,
-the flow kernel with named-barrier hand-offs and the polled form) and the same graph with
+k_flow_tc as one launch per flow and as one launch per layer) and the same graph with
 cond_upsample_method='transposed_conv'. Prints max|delta| vs the oracle (the checker; not the thing checked)."""
 import importlib, os, sys
 import numpy as np, torch
@@ -23,10 +23,10 @@ for method in ('repeat', 'transposed_conv'):
     d = W.model_dims(hp)
     noise, mel = O.synthetic_inputs(n, t, 80, 80)
     ref = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], dtype=np.float64)
-    for precision, quiet in (('f16x3', '1'), ('f16x3', '0'), ('bf16', '1'), ('fp32', '1')):
-        os.environ['PWV_TC_QUIET'] = quiet
+    for precision, quiet in (('f16x3', '100'), ('f16x3', '1'), ('bf16', '100'), ('fp32', '0')):    # second field: PWV_TC_SEG
+        os.environ['PWV_TC_SEG'] = quiet
         model = V.PwvModel(d, weights, precision)
         out = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
         torch.cuda.synchronize()
-        print(method, precision, 'quiet=' + quiet, 'max|delta|', float(np.abs(out.cpu().numpy() - ref).max()), flush=True)
+        print(method, precision, 'seg=' + quiet, 'max|delta|', float(np.abs(out.cpu().numpy() - ref).max()), flush=True)
         del model

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Which launch form of the gated layers is faster at which job size? One process, default hparams, T = 16000:
 for every batch size N and arithmetic mode, the c2-style timed loop (L2 flushed before every step, CUDA events) with
-  pdl   : one k_layer_tc launch per layer, programmatic dependent launch, no tile flags (PWV_NO_TILE_FLAGS=1)
-  flow  : one persistent k_flow_tc launch per flow, tiles chained by flags (the default)
+  pdl    : one k_layer_tc launch per layer (640 threads, polled mbarriers), programmatic dependent launch, no tile flags
+  layers : one k_flow_tc launch per layer (PWV_TC_SEG=1; 512-thread form unless PWV_TC_QUIET=0)
+  flow   : one persistent k_flow_tc launch per flow, tiles chained by flags (PWV_TC_SEG=100)
 usage: sweep_modes.py [N,N,...] [T]   -> one JSON line per (N, precision, mode) on stdout"""
 import importlib, json, os, sys
 import numpy as np, torch
@@ -19,7 +20,7 @@ hp.set_hparam_yaml('bench/c2')
 weights = W.init_weights(hp, seed=0)
 dims = W.model_dims(hp)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-MODES = {'pdl': {'PWV_NO_TILE_FLAGS': '1'}, 'flow': {}}
+MODES = {'pdl': {'PWV_NO_TILE_FLAGS': '1'}, 'layers': {'PWV_TC_SEG': '1'}, 'flow': {'PWV_TC_SEG': '100'}}
 for n in ns:
     noise, mel = O.synthetic_inputs(n, t, 80, 80)
     noise, mel = torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()
@@ -27,7 +28,7 @@ for n in ns:
     for prec in ('f16x3', 'bf16'):
         res = {}
         for mode, env in MODES.items():
-            for k in ('PWV_NO_TILE_FLAGS', 'PWV_TC_FLOW'):
+            for k in ('PWV_NO_TILE_FLAGS', 'PWV_TC_FLOW', 'PWV_TC_SEG'):
                 os.environ.pop(k, None)
             os.environ.update(env)
             m = V.PwvModel(dims, weights, prec)
@@ -44,4 +45,5 @@ for n in ns:
             res[mode] = ms
             del m
         print(json.dumps({'N': n, 'T': t, 'precision': prec, 'tiles_per_cta_layer': round(n * ((t + 127) // 128) / 74, 1),
-                          'ms_pdl': round(res['pdl'], 4), 'ms_flow': round(res['flow'], 4), 'flow_over_pdl': round(res['flow'] / res['pdl'], 4)}), flush=True)
+                          'ms_pdl': round(res['pdl'], 4), 'ms_layers': round(res['layers'], 4), 'ms_flow': round(res['flow'], 4),
+                          'best': min(res, key=res.get), 'samples_per_s_best': round(n * t / min(res.values()) * 1e3)}), flush=True)
