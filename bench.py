@@ -316,7 +316,8 @@ def main():
     total_ms = float(total_ms.item())
     samples_per_step = n * t * world
     value = samples_per_step * args.steps / (total_ms * 1e-3)
-    launches = model.last_launch_count() * args.steps
+    launches_per_forward = model.last_launch_count()
+    launches = launches_per_forward * args.steps
 
     # ---- roofline of the dominant kernel (gated dilated layer), separate profiled steps
     pk = peaks()
@@ -347,9 +348,11 @@ def main():
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get(precision, {}).get('dram_bytes_per_launch')
+            tj = json.load(fh)
+            key = precision + '_layers' if (launches_per_forward >= n_gated and precision + '_layers' in tj) else precision
+            traffic = tj.get(key, {}).get('dram_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
-                'traffic': traffic, 'peak_source': pk['source'], 'kernel': 'gated dilated layers in k_flow_tc (tcgen05; one persistent launch per flow, both bodies; figures per gated layer)' if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
+                'traffic': traffic, 'peak_source': pk['source'], 'kernel': ('gated dilated layers in k_flow_tc (tcgen05; one persistent launch per flow, both bodies; figures per gated layer)' if launches_per_forward < n_gated else 'gated dilated layer k_layer_tc (tcgen05, both bodies per launch; one launch per layer, programmatic dependent launch)') if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
                 'bytes_per_launch': n_gated * bytes_per_layer / max(layer_n, 1), 'avg_launch_us': layer_s * 1e6 / max(layer_n, 1),
                 'isolated_launch_us': float(np.median(iso_ms)) * 1e3 / max(iso_n, 1),
                 'frac_isolated': n_gated * bytes_per_layer / (float(np.median(iso_ms)) * 1e-3) / 1e9 / pk['hbm'],
