@@ -733,7 +733,9 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   const double tiles_per_cta = (double)tiles_body / (grid / 2);
   const bool in_window = tiles_per_cta >= 2.5 && tiles_per_cta <= 17.0;
   const bool flow_kernel = m->use_flow && m->use_flags && m->tc_variant == 0 && m->profiling != 1 && !tap_layer && (!m->trace || getenv("PWV_TRACE_FLOW")) &&
-                           L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms && (m->tc_seg > 0 || in_window);
+                           L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms && (m->tc_seg > 0 || (in_window && c_hop > 1));
+  // (c_hop == 1: full-rate conditioning rows, cond_upsample_method 'transposed_conv' -- read from global memory per row;
+  //  that combination is verified on the per-layer kernels only)
   // tile flags between per-layer launches only pay in the same window (the A/B form PWV_TC_FLOW=0)
   const bool layer_flags = m->use_flags && (in_window || m->tc_seg > 0);
   if (flow_kernel) {
