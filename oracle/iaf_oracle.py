@@ -50,6 +50,10 @@ class NumpyOps:
     def to_numpy(x):
         return x
 
+    @staticmethod
+    def moments_time(x):
+        return x.mean(axis=1, keepdims=True), x.var(axis=1, keepdims=True)
+
 
 class TorchOps:
     """Same restatement evaluated by torch's CPU kernels (MKL matmul, threaded elementwise): the
@@ -70,6 +74,10 @@ class TorchOps:
     @staticmethod
     def to_numpy(x):
         return x.numpy()
+
+    @staticmethod
+    def moments_time(x):
+        return x.mean(dim=1, keepdim=True), x.var(dim=1, keepdim=True, unbiased=False)
 
 
 _OPS = NumpyOps()
@@ -134,6 +142,23 @@ def conv1x1(x, w):
     return x @ w[0]
 
 
+# ----------------------------------------------------------------------------- normalisers
+def instance_normalization(x, gamma, beta, epsilon=1e-8):
+    """Reference modules.py:274-284: per utterance and channel, mean / (population) variance over the TIME axis,
+    (x - mean) / (variance + 1e-8) ** .5, then gamma * . + beta."""
+    mean, variance = _OPS.moments_time(x)                                    # :278
+    return gamma * ((x - mean) / ((variance + epsilon) ** .5)) + beta        # :282-283
+
+
+def normalize(x, W, scope):
+    """Reference modules.py:263-270 at the call site whose variable scope is `scope`. Which method the graph was
+    built with is read off the weight container: method 'in' creates `<scope>/beta`, `<scope>/gamma`; method ''
+    creates nothing and is the identity. ('bn' is not restated: tf.layers.batch_normalization lives in TensorFlow.)"""
+    if scope + '/gamma' in W:
+        return instance_normalization(x, W[scope + '/gamma'], W[scope + '/beta'])
+    return x
+
+
 # ----------------------------------------------------------------------------- WaveNet body
 def _tanh(x):
     return _OPS.tanh(x)
@@ -144,7 +169,7 @@ def _sigmoid(x):
 
 
 def dilation_layer(cur, cond, W, prefix, dilation, use_biases):
-    """Reference modules.py:185-259 with normalize off. Returns (skip_output, dense_output, z)."""
+    """Reference modules.py:185-259. Returns (skip_output, dense_output, z)."""
     f = causal_conv(cur, W[prefix + '/filter'], dilation)                    # :213
     g = causal_conv(cur, W[prefix + '/gate'], dilation)                      # :214
     if cond is not None:
@@ -153,18 +178,24 @@ def dilation_layer(cur, cond, W, prefix, dilation, use_biases):
     if use_biases:
         f = f + W[prefix + '/filter_bias']                                   # :227
         g = g + W[prefix + '/gate_bias']                                     # :228
+    f = normalize(f, W, prefix + '/normalize_filter')                        # :230-232
+    g = normalize(g, W, prefix + '/normalize_gate')                          # :233-234
     z = _tanh(f) * _sigmoid(g)                                               # :236
     transformed = conv1x1(z, W[prefix + '/dense'])                           # :239-240
     skip = conv1x1(z, W[prefix + '/skip'])                                   # :243-244
     if use_biases:
         transformed = transformed + W[prefix + '/dense_bias']                # :249
         skip = skip + W[prefix + '/skip_bias']                               # :250
-    return skip, cur + transformed, z                                        # :251,259
+    dense_output = cur + transformed                                         # :251
+    skip = normalize(skip, W, prefix + '/normalize_skip_output')             # :253-255
+    dense_output = normalize(dense_output, W, prefix + '/normalize_dense_output')    # :256-257
+    return skip, dense_output, z                                             # :259
 
 
 def wavenet(x, cond, W, prefix, dilations, use_biases=True, use_skip_connection=False, taps=None):
     """Reference modules.py:129-166, WaveNet.__call__. x (N,T,1), cond (N,T,Cc) -> (N,T,1)."""
     cur = causal_conv(x, W[prefix + '/causal_layer/filter'], 1)              # :133-134,174-183 (no bias)
+    cur = normalize(cur, W, prefix + '/causal_layer/normalize')              # :181-182
     if taps is not None:
         taps[prefix + '/causal_layer'] = cur
     outputs = []
@@ -180,10 +211,12 @@ def wavenet(x, cond, W, prefix, dilations, use_biases=True, use_skip_connection=
     else:
         total = outputs[-1]
     h = _OPS.relu(total)                                                     # :148
+    h = normalize(h, W, prefix + '/postprocessing/normalize_postprocess1')   # :149-151
     h = conv1x1(h, W[prefix + '/postprocessing/postprocess1'])               # :152-153
     if use_biases:
         h = h + W[prefix + '/postprocessing/postprocess1_bias']              # :155-156
     h = _OPS.relu(h)                                                         # :157
+    h = normalize(h, W, prefix + '/postprocessing/normalize_postprocess2')   # :158-160
     y = conv1x1(h, W[prefix + '/postprocessing/postprocess2'])               # :161-162
     if use_biases:
         y = y + W[prefix + '/postprocessing/postprocess2_bias']              # :164-165
@@ -216,6 +249,11 @@ def upsample_cond_transposed(mel, W, strides, hop):
         cout = w.shape[2]
         out = cond.reshape(n * length, cin) @ w[0].reshape(stride * cout, cin).T       # [n*len, stride*cout]
         cond = _OPS.relu(out.reshape(n, length * stride, cout))                        # :118-120
+        # :121-122 -- the reference normalises the 4-D tensor (n, 1, length, C) and instance_normalization's
+        # "time axis" is axis 1 (modules.py:277), here the dummy height of size 1: mean = x, variance = 0, so the
+        # stage's output collapses to beta. Replayed literally (a quirk of the reference, not of this restatement).
+        cond = normalize(cond.reshape(n, 1, length * stride, cout), W,
+                         f'{ROOT}/cond/normalize_transposed_conv_{i}').reshape(n, length * stride, cout)
     return cond[:, hop // 2: -hop // 2, :]                                   # :124
 
 
@@ -228,7 +266,8 @@ def logistic_noise(shape, seed, dtype=np.float64):
 
 def iaf_vocoder_forward(noise, mel, W, dilations, hop, use_biases=True, use_skip_connection=False,
                         dtype=np.float64, taps=None, ops=None):
-    """Reference models.py:23-78 (is_training=False, normalizers '', upsample 'repeat').
+    """Reference models.py:23-78 (is_training=False; conditioning upsampled by 'repeat' or 'transposed_conv' and the
+    normalisers '' or 'in', all read off the variables present in W).
 
     noise (N,T) or (N,T,1): the logistic sample the reference draws in-graph (models.py:32-33) --
     an INPUT here so that both sides see the same numbers. mel (N, 1+T//hop, n_mels).
@@ -251,6 +290,7 @@ def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dty
         cond = upsample_cond_repeat(mel, W[f'{ROOT}/cond/dense'], hop)       # models.py:26,127-133
     else:
         cond = upsample_cond_transposed(mel, W, UPSAMPLE_STRIDES, hop)       # models.py:26,109-124
+    cond = normalize(cond, W, f'{ROOT}/cond/normalize/normalize')            # models.py:27-29 (after the crop)
     if cond.shape[1] != t:
         raise ValueError(f'cond length {cond.shape[1]} != {t}: length must be a multiple of hop '
                          f'and mel must have 1 + length//hop frames')
@@ -259,6 +299,7 @@ def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dty
         scale = wavenet(x, cond, W, p + '/scalar', dil, use_biases, use_skip_connection, taps)
         shift = wavenet(x, cond, W, p + '/shifter', dil, use_biases, use_skip_connection, taps)
         x = x * scale + shift                                                # modules.py:57-59
+        x = normalize(x, W, f'{ROOT}/normalize{i}')                          # models.py:70
         if taps is not None:
             taps[p] = _OPS.to_numpy(x[:, :, 0]).copy()
     return x[:, :, 0]

@@ -15,6 +15,17 @@ import numpy as np
 float32 = np.float32
 AUTO_REUSE = object()
 
+
+class _T(np.ndarray):
+    """ndarray with the one Tensor method the reference calls on activations (modules.py:275: input.get_shape())."""
+
+    def get_shape(self):
+        return tuple(int(s) for s in self.shape)
+
+
+def _t(x):
+    return np.asarray(x).view(_T)
+
 _scope = []
 _variables = {}
 _created = []          # names in creation order (the reference's variable list)
@@ -64,7 +75,7 @@ def get_variable(name, shape=None, initializer=None, trainable=True, **_):
         raise ValueError('tf_shim: %s has shape %s, graph asks for %s' % (full, value.shape, tuple(shape)))
     if full not in _created:
         _created.append(full)
-    return value
+    return _t(value)
 
 
 def trainable_variables(scope=None):
@@ -88,46 +99,46 @@ def div(a, b):
 
 
 def pad(value, paddings, **_):
-    return np.pad(value, [tuple(int(v) for v in p) for p in paddings])
+    return _t(np.pad(value, [tuple(int(v) for v in p) for p in paddings]))
 
 
 def reshape(x, shape, **_):
-    return np.reshape(x, [int(s) for s in shape])
+    return _t(np.reshape(x, [int(s) for s in shape]))
 
 
 def transpose(x, perm=None, **_):
-    return np.transpose(x, perm)
+    return _t(np.transpose(x, perm))
 
 
 def slice(x, begin, size, **_):     # noqa: A001 (mirrors tf.slice)
     idx = []
     for b, s, dim in zip(begin, size, np.shape(x)):
         idx.append(np.s_[int(b):(dim if int(s) == -1 else int(b) + int(s))])
-    return x[tuple(idx)]
+    return _t(x[tuple(idx)])
 
 
 def tile(x, multiples, **_):
-    return np.tile(x, [int(m) for m in multiples])
+    return _t(np.tile(x, [int(m) for m in multiples]))
 
 
 def expand_dims(x, axis, **_):
-    return np.expand_dims(x, axis)
+    return _t(np.expand_dims(x, axis))
 
 
 def squeeze(x, axis=None, **_):
-    return np.squeeze(x, axis)
+    return _t(np.squeeze(x, axis))
 
 
 def tanh(x, **_):
-    return np.tanh(x)
+    return _t(np.tanh(x))
 
 
 def sigmoid(x, **_):
-    return 1.0 / (1.0 + np.exp(-x))
+    return _t(1.0 / (1.0 + np.exp(-x)))
 
 
 def add(a, b, **_):
-    return a + b
+    return _t(a + b)
 
 
 def _conv1d(value, filters, stride=1, padding='VALID', name=None, **_):
@@ -144,11 +155,11 @@ def _conv1d(value, filters, stride=1, padding='VALID', name=None, **_):
     out = np.zeros((value.shape[0], t_out, filters.shape[2]), dtype=np.result_type(value, filters))
     for j in range(k):
         out = out + np.einsum('ntc,co->nto', value[:, j:j + t_out, :], filters[j])
-    return out
+    return _t(out)
 
 
 def _relu(x, **_):
-    return np.maximum(x, 0)
+    return _t(np.maximum(x, 0))
 
 
 def _conv2d_transpose(value, filter, output_shape, strides, padding='SAME', **_):   # noqa: A002 (mirrors tf)
@@ -170,10 +181,16 @@ def _conv2d_transpose(value, filter, output_shape, strides, padding='SAME', **_)
         full[:, 0, j:j + (w_in - 1) * s + 1:s, :] += np.einsum('nlc,oc->nlo', value[:, 0], filter[0, j])
     if full.shape[2] < out_w + pad_left:       # kernel narrower than the stride: untouched positions stay zero
         full = np.pad(full, [(0, 0), (0, 0), (0, out_w + pad_left - full.shape[2]), (0, 0)])
-    return full[:, :, pad_left:pad_left + out_w, :]
+    return _t(full[:, :, pad_left:pad_left + out_w, :])
 
 
-nn = types.SimpleNamespace(conv1d=_conv1d, relu=_relu, conv2d_transpose=_conv2d_transpose)
+def _moments(x, axes, keep_dims=False, **_):
+    """tf.nn.moments: mean and (population) variance over `axes`."""
+    axes = tuple(int(a) for a in axes)
+    return _t(np.mean(x, axis=axes, keepdims=keep_dims)), _t(np.var(x, axis=axes, keepdims=keep_dims))
+
+
+nn = types.SimpleNamespace(conv1d=_conv1d, relu=_relu, conv2d_transpose=_conv2d_transpose, moments=_moments)
 
 
 class _EMA(object):
@@ -198,7 +215,7 @@ class _Logistic(object):
         s = _logistic_sample[0]
         if s is None:
             raise RuntimeError('tf_shim: set_logistic_sample() first')
-        return np.reshape(s, [int(v) for v in shape])
+        return _t(np.reshape(s, [int(v) for v in shape]))
 
 
 from . import contrib  # noqa: E402  (tensorflow.contrib.{distributions,signal})

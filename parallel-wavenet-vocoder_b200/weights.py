@@ -25,7 +25,11 @@ def model_dims(hp):
                 dilations=[list(map(int, d)) for d in m.dilations[:int(m.n_iaf)]],
                 use_biases=bool(m.use_biases), use_skip=bool(m.use_skip_connection),
                 cond_upsample=str(m.get('cond_upsample_method', 'repeat') or 'repeat'),
-                upsample_strides=list(UPSAMPLE_STRIDES))
+                upsample_strides=list(UPSAMPLE_STRIDES),
+                # normalisers (reference modules.py:263-284): '' off; the weight container and the oracle know 'in'
+                # (instance normalisation over time); the B200 path itself rejects every non-empty value (vocoder.py)
+                norm_flow=str(m.get('normalize', '') or ''), norm_cond=str(m.get('normalize_cond', '') or ''),
+                norm_wavenet=str(m.get('normalize_wavenet', '') or ''))
 
 
 def variable_shapes(hp):
@@ -33,17 +37,30 @@ def variable_shapes(hp):
     d = model_dims(hp)
     k, R, D, S, Cc = d['k'], d['R'], d['D'], d['S'], d['Cc']
     shapes = OrderedDict()
+    for key in ('norm_flow', 'norm_cond', 'norm_wavenet'):
+        if d[key] not in ('', 'in'):
+            raise NotImplementedError(f"normaliser {d[key]!r}: only '' and 'in' have a variable layout here "
+                                      f"(reference modules.py:263-284; 'bn' creates tf.layers variables)")
+
+    def norm(scope, channels, on):      # instance_normalization's variables, beta before gamma (modules.py:279-280)
+        if on:
+            shapes[f'{scope}/beta'] = (channels,)
+            shapes[f'{scope}/gamma'] = (channels,)
+    nc, nw, nf = d['norm_cond'] == 'in', d['norm_wavenet'] == 'in', d['norm_flow'] == 'in'
     if d['cond_upsample'] == 'transposed_conv':     # reference models.py:109-124: [1, stride, Cc (out), Cin]
         cin = d['n_mels']
         for i, stride in enumerate(d['upsample_strides']):
             shapes[f'{ROOT}/cond/transposed_conv_{i}_weights'] = (1, stride, Cc, cin)
+            norm(f'{ROOT}/cond/normalize_transposed_conv_{i}', Cc, nc)       # models.py:121-122
             cin = Cc
     else:
         shapes[f'{ROOT}/cond/dense'] = (1, d['n_mels'], Cc)
+    norm(f'{ROOT}/cond/normalize/normalize', Cc, nc)                         # models.py:27-29
     for i in range(d['n_iaf']):
         for body in BODIES:
             p = f'{ROOT}/iaf{i}/{body}'
             shapes[f'{p}/causal_layer/filter'] = (k, 1, R)
+            norm(f'{p}/causal_layer/normalize', R, nw)                       # modules.py:181-182
             for j, _ in enumerate(d['dilations'][i]):
                 q = f'{p}/dilated_stack/layer{j}'
                 shapes[f'{q}/filter'] = (k, R, D)
@@ -53,18 +70,25 @@ def variable_shapes(hp):
                 if d['use_biases']:
                     shapes[f'{q}/filter_bias'] = (D,)
                     shapes[f'{q}/gate_bias'] = (D,)
+                norm(f'{q}/normalize_filter', D, nw)                         # modules.py:230-234
+                norm(f'{q}/normalize_gate', D, nw)
                 shapes[f'{q}/dense'] = (1, D, R)
                 shapes[f'{q}/skip'] = (1, D, S)
                 if d['use_biases']:
                     shapes[f'{q}/dense_bias'] = (R,)
                     shapes[f'{q}/skip_bias'] = (S,)
+                norm(f'{q}/normalize_skip_output', S, nw)                    # modules.py:253-257
+                norm(f'{q}/normalize_dense_output', R, nw)
             q = f'{p}/postprocessing'
+            norm(f'{q}/normalize_postprocess1', S, nw)                       # modules.py:149-151
             shapes[f'{q}/postprocess1'] = (1, S, S)
             if d['use_biases']:
                 shapes[f'{q}/postprocess1_bias'] = (S,)
+            norm(f'{q}/normalize_postprocess2', S, nw)                       # modules.py:158-160
             shapes[f'{q}/postprocess2'] = (1, S, 1)
             if d['use_biases']:
                 shapes[f'{q}/postprocess2_bias'] = (1,)
+        norm(f'{ROOT}/normalize{i}', 1, nf)                                  # models.py:70
     return shapes
 
 
@@ -87,6 +111,8 @@ def init_weights(hp, seed=0, bias_std=0.0, gain=1.0, dtype=np.float32):
     for name, shape in variable_shapes(hp).items():
         if len(shape) == 1:
             w = rng.normal(0.0, bias_std, size=shape) if bias_std > 0 else np.zeros(shape)
+            if name.endswith('/gamma'):        # instance-norm scale: tf.ones_initializer (modules.py:280), jittered like the biases
+                w = w + 1.0
         elif len(shape) == 4:            # conv2d_transpose filter [1, width, Cout, Cin]
             _, width, cout, cin = shape
             limit = np.sqrt(6.0 / (width * cin + width * cout))

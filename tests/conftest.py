@@ -47,6 +47,8 @@ def load_golden(hp, name):
     model = {'n_iaf': int(g['n_iaf']), 'dilations': dil}
     if 'cond_upsample_method' in g.files:
         model['cond_upsample_method'] = str(g['cond_upsample_method'])
+    if 'normalize' in g.files:          # every normaliser call site (reference modules.py:263-284)
+        model.update({'normalize': str(g['normalize']), 'normalize_cond': str(g['normalize']), 'normalize_wavenet': str(g['normalize'])})
     hp.set_hparam_dict({'model': model}, case='golden/' + name)
     seed, bias_std, gain = g['weight_recipe']
     weights = pkg('weights').init_weights(hp, seed=int(seed), bias_std=float(bias_std), gain=float(gain))

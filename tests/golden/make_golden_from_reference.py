@@ -9,7 +9,7 @@ in the reference's Python. What they do not pin: TensorFlow's kernels (restated 
 
     python tests/golden/make_golden_from_reference.py
 
-writes tests/golden/ref_tran.npz (cond_upsample_method 'transposed_conv'), tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
+writes tests/golden/ref_norm.npz / ref_norm_tran.npz (all normalisers 'in'), tests/golden/ref_tran.npz (cond_upsample_method 'transposed_conv'), tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
 inputs and weights, non-zero biases), tests/golden/ref_flows.npz (a 2-flow graph with per-flow
 outputs) and tests/golden/ref_varlist.txt (the graph's variable names in creation order).
 """
@@ -139,6 +139,32 @@ def main():
     d = pack(noise, mel, wav, weights, dil, (45, 0.1, 1.0))
     d['cond_upsample_method'] = np.array('transposed_conv')
     np.savez_compressed(os.path.join(HERE, 'ref_tran.npz'), **d)
+    ref_hp.model.cond_upsample_method = 'repeat'
+
+    # ---- fixtures 5, 6: every normaliser call site switched to 'in' (reference modules.py:263-284: instance
+    #      normalisation over time, executed from the reference's own instance_normalization), with 'repeat' and with
+    #      'transposed_conv' conditioning (where the reference normalises a 4-D tensor over its size-1 axis, so each
+    #      stage's output collapses to beta -- replayed literally by the oracle). The B200 path rejects these options;
+    #      the fixtures pin the oracle for them.
+    norm = {'normalize': 'in', 'normalize_cond': 'in', 'normalize_wavenet': 'in'}
+    for method, fname, seed in (('repeat', 'ref_norm.npz', 46), ('transposed_conv', 'ref_norm_tran.npz', 47)):
+        for key, val in norm.items():
+            setattr(ref_hp.model, key, val)
+        ref_hp.model.cond_upsample_method = method
+        my_hp.set_hparam_dict({'model': dict(norm, n_iaf=2, dilations=dil, cond_upsample_method=method)}, case='golden/' + fname)
+        weights = W.init_weights(my_hp, seed=seed, bias_std=0.1, dtype=np.float32)
+        wav, created = run_reference(tf, ref_models, weights, noise, mel)
+        assert created == list(W.variable_shapes(my_hp).keys()), 'variable list / creation order differs (normalisers, %s)' % method
+        ours = O.iaf_vocoder_forward(noise, mel, weights, dil, hop, dtype=np.float64)
+        err = np.abs(ours - wav).max()
+        print('instance-norm graph (%s): reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (method, err, np.abs(wav).max()))
+        assert err < 1e-11
+        d = pack(noise, mel, wav, weights, dil, (seed, 0.1, 1.0))
+        d['cond_upsample_method'] = np.array(method)
+        d['normalize'] = np.array('in')
+        np.savez_compressed(os.path.join(HERE, fname), **d)
+        for key in norm:
+            setattr(ref_hp.model, key, '')
     ref_hp.model.cond_upsample_method = 'repeat'
     print('wrote ref_small.npz, ref_flows.npz, ref_varlist.txt (%d variables in the default graph)' % len(W.variable_shapes(my_hp.set_hparam_yaml('default'))))
 

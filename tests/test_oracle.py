@@ -9,7 +9,7 @@ from conftest import ROOT, load_golden, pkg, small_case
 from oracle import iaf_oracle as O
 
 
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz', 'ref_norm.npz', 'ref_norm_tran.npz'])
 def test_oracle_reproduces_reference_golden(hp, name):
     weights, noise, mel, wav, dil = load_golden(hp, name)
     skip = name == 'ref_skip.npz'        # generated with model.use_skip_connection=True
@@ -73,3 +73,27 @@ def test_length_must_be_multiple_of_hop(hp):
     mel = np.zeros((1, 2, 80), np.float32)
     with pytest.raises(ValueError):
         O.iaf_vocoder_forward(noise, mel, weights, hp.model.dilations, 80)
+
+
+def test_instance_norm_variables_and_rejection_on_the_product_path(hp):
+    """With every normaliser set to 'in' the weight container lists the reference's beta/gamma variables at each call
+    site (order pinned by the fixture generator against the reference's own graph code), the oracle normalises per
+    utterance and channel over time -- and the B200 path refuses the option instead of ignoring it."""
+    small_case(hp, dilations=((1, 2), (4,)), n=2, t=160, precision='fp32')
+    hp.model.normalize = hp.model.normalize_cond = hp.model.normalize_wavenet = 'in'
+    W = pkg('weights')
+    names = list(W.variable_shapes(hp).keys())
+    assert 'iaf_vocoder/cond/normalize/normalize/beta' in names and 'iaf_vocoder/normalize1/gamma' in names
+    assert names.index('iaf_vocoder/iaf0/scalar/dilated_stack/layer0/normalize_filter/beta') == \
+        names.index('iaf_vocoder/iaf0/scalar/dilated_stack/layer0/gate_bias') + 1
+    weights = W.init_weights(hp, seed=3, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(2, 160, 80, 80)
+    out = O.iaf_vocoder_forward(noise, mel, weights, [[1, 2], [4]], 80, dtype=np.float64)
+    # the last flow's output went through normalize1: per utterance mean = beta, std = |gamma| (up to the 1e-8 epsilon)
+    beta, gamma = float(weights['iaf_vocoder/normalize1/beta'][0]), float(weights['iaf_vocoder/normalize1/gamma'][0])
+    assert np.allclose(out.mean(axis=1), beta, atol=1e-9) and np.allclose(out.std(axis=1), abs(gamma), rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        pkg('vocoder')._assert_supported(hp)
+    with pytest.raises(NotImplementedError):          # 'bn' has no variable layout here
+        hp.model.normalize = 'bn'
+        W.variable_shapes(hp)
