@@ -4,17 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # this build (sm_100a kernels)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
 
-One "step" = one forward pass (noise + mel -> waveform, 4 IAF flows) over one batch. Workload at
-N=1: BASELINE.json configs[1] ("c2": batch = 8 utterances x 1 s @ 16 kHz, default hparams, fp32).
-N>1: the same batch PER GPU (weak scaling; utterances are independent, no data-path collective),
-launched by torchrun with one rank per GPU.
+One "step" = one forward pass (noise + mel -> waveform, 4 IAF flows) over one batch.
+Workload: N=1 -> BASELINE.json configs[1] ("c2": batch = 8 utterances x 1 s @ 16 kHz, default hparams,
+fp32-parity arithmetic); N>1 -> configs[3] ("c4": 256 utterances x 1 s sharded over the N GPUs, 256/N
+per GPU: the config the whole-box metric is quoted on; strong scaling, utterances are independent, no
+data-path collective), launched by torchrun with one rank per GPU. `--workload` overrides.
 
 Prints ONE JSON line (rank 0). `value` = whole-job samples/s with inputs resident in HBM, timed
-with CUDA events per step (L2 flushed between steps), max over ranks. `e2e` = the same metric
-through the C-ABI host-buffer call `pwv_forward_host` (pinned host inputs, H2D + kernels + D2H +
-sync inside the timed region). `roofline` = the gated-layer kernel's algorithmic bytes / its
-measured launch time against MEASURED_PEAKS.json. `cpu_baseline` = the numpy oracle (a port of
-the reference's TF-CPU path; TF itself is not installable) timed on this box's host cores.
+with CUDA events per step (L2 flushed between steps), max over ranks. `sustained` = the same forward
+back to back for >= 1.5 s (the power-capped regime a 60 ms timed region never sees). `e2e` = the same
+metric through the C-ABI host-buffer call `pwv_forward_host` (pinned host inputs, H2D + kernels + D2H +
+sync inside the timed region); at N>1 every rank runs it on its own shard of ONE shared pinned host batch.
+`roofline` = the gated-layer kernel's algorithmic bytes / its measured launch time against
+MEASURED_PEAKS.json. `cpu_baseline` = the numpy oracle (a port of the reference's TF-CPU path; TF itself
+is not installable) timed on this box's host cores. Both arms print the same `config`.
 """
 import argparse
 import importlib
@@ -39,8 +42,22 @@ WORKLOADS = {
     'c1': ('bench/c1', 'c1: batch=1 utt x 1 s (16000 samples), 16 kHz, default hparams'),
     'c2': ('bench/c2', 'c2: batch=8 utt x 1 s (16000 samples) per GPU, 16 kHz, 4 IAF flows, default hparams'),
     'c3': ('bench/c3', 'c3: batch=64 utt x 4 s (96000 samples) per GPU, 24 kHz, default hparams'),
-    'c4': ('bench/c4', 'c4: batch=256 utt x 1 s total, sharded over the GPUs'),
+    'c4': ('bench/c4', 'c4: batch=256 utt x 1 s (16000 samples) total, sharded over the GPUs (256/N per GPU), 16 kHz, 4 IAF flows, default hparams'),
 }
+
+
+def default_workload(world):
+    return 'c2' if world == 1 else 'c4'
+
+
+def workload_config(name, hp, world):
+    """The `config` object both arms print: what is computed, nothing about how."""
+    n_total, t = int(hp.generate.batch_size), int(hp.generate.length)
+    strong = name == 'c4'
+    return {'workload': WORKLOADS[name][1], 'utterances_per_step_whole_job': n_total if strong else n_total * world,
+            'length': t, 'sr': int(hp.signal.sr), 'n_gpus': world, 'hparams': 'hparams/default.yaml',
+            'l2': 'GPU arm: flushed (256 MB write) before every timed step',
+            'timing': 'GPU arm: CUDA events per step, max over ranks; CPU arm: perf_counter per step'}
 
 
 def pkg(mod):
@@ -179,25 +196,29 @@ def time_cpu_oracle(hp, n, t, repeats=1, warm=False):
 def run_reference_arm(args, hp, rank, world):
     """`--impl reference`: the reference's CPU implementation of the path. TensorFlow 1.x cannot be
     installed (no wheel for this Python, no network), so this is the oracle port, on all host
-    cores, one bounded sample (1 utterance of the workload's length) per step."""
+    cores. A step = the GPU arm's batch when that is the c1/c2 batch; for the bigger workloads a bounded
+    sample of it (8 utterances of the workload's length, at most 16000 samples each) so that the run ends
+    within minutes."""
     if rank != 0:
         return
-    n_s, t = 1, int(hp.generate.length)
-    t = min(t, 16000)
+    n_total, t = int(hp.generate.batch_size), int(hp.generate.length)
+    n_s, t_s = min(n_total, 8), min(t, 16000)
     for _ in range(max(args.warmup, 0) and 1):      # one warm-up pass is enough for BLAS thread start
         time_cpu_oracle(hp, 1, 1600)
-    _, times = time_cpu_oracle(hp, n_s, t, repeats=args.steps)
+    _, times = time_cpu_oracle(hp, n_s, t_s, repeats=args.steps)
     total = float(sum(times))
-    value = n_s * t * len(times) / total
+    value = n_s * t_s * len(times) / total
     cores = _THREADS.get('best', host_cores())
+    whole = (n_s, t_s) == (n_total, t)
     line = {
         'impl': 'reference', 'metric': 'audio_samples_per_sec', 'value': value, 'unit': 'samples/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOADS[args.workload][1], 'sample': f'{n_s} utterance x {t} samples per step',
-                   'note': 'oracle port of the reference TF-CPU forward (oracle/iaf_oracle.py on torch-CPU kernels, all host threads); TF 1.x not installable'},
+        'higher_is_better': True, 'scaling': 'strong' if args.workload == 'c4' else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, hp, world),
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'cores_available': host_cores(), 'kind': 'port',
-                         'sample': f'{len(times)} x ({n_s} utt x {t} samples), default hparams, fp32'},
+                         'sample': (f'{len(times)} x the whole step batch ({n_s} utt x {t_s} samples)' if whole else
+                                    f'{len(times)} x a bounded sample of the step batch ({n_s} of {n_total} utt x {t_s} of {t} samples)') +
+                                   ', default hparams, fp32; oracle port of the reference TF-CPU forward (oracle/iaf_oracle.py on torch-CPU kernels); TF 1.x not installable'},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -223,6 +244,28 @@ class StdoutGuard:
         os.dup2(2, 1)
 
 
+def src_sha16(rel):
+    import hashlib
+    with open(os.path.join(ROOT, rel), 'rb') as fh:
+        return hashlib.sha256(fh.read()).hexdigest()[:16]
+
+
+def measured_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None
+    when that capture was taken from a different revision of the kernel source (a stale figure is worse than none)."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None, 'no ncu capture committed'
+    with open(path) as fh:
+        tj = json.load(fh)
+    ent = tj.get(kernel_key)
+    if not ent:
+        return None, f'no ncu capture of {kernel_key}'
+    if ent.get('src_sha16') != src_sha16(ent.get('src', PKG + '/csrc/pwv_tc2.cuh')):
+        return None, f'ncu capture of {kernel_key} predates the current kernel source'
+    return ent.get('dram_bytes_per_launch'), ent.get('capture')
+
+
 def main():
     guard = StdoutGuard()
     ap = argparse.ArgumentParser()
@@ -230,20 +273,27 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS), help='default: c2 on 1 GPU, c4 on N > 1')
     ap.add_argument('--precision', default=None, help="override engine.precision: fp32 | f16x3 | bf16")
-    ap.add_argument('--tc-variant', type=int, default=None, help='gated-layer kernel variant (PWV_TC_VARIANT: 0 | 1 | 2), A/B runs')
+    ap.add_argument('--debug', action='append', default=[], metavar='KEY=INT', help='pwv_debug_set switch (A/B runs), repeatable')
+    ap.add_argument('--e2e-mode', default='hostshard', choices=['hostshard', 'nccl'],
+                    help='N > 1: shared pinned host batch, every rank copies its own shard (default) | rank-0 H2D + NCCL scatter/gather')
+    ap.add_argument('--sustain-s', type=float, default=1.5, help='seconds of back-to-back forwards for the sustained leg (0: off)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
-    if args.tc_variant is not None:
-        os.environ['PWV_TC_VARIANT'] = str(args.tc_variant)
+    debug = {}
+    for kv in args.debug:
+        k, _, v = kv.partition('=')
+        debug[k] = int(v)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.workload is None:
+        args.workload = default_workload(world)
     hp = pkg('hparam').hparam
     hp.set_hparam_yaml(WORKLOADS[args.workload][0])
 
@@ -261,22 +311,22 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout carries ONE JSON line
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', '') and not os.environ.get('PWV_KEEP_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', device_id=dev)      # (NCCL's log lines go wherever NCCL_DEBUG sends them; fd 1 is guarded)
     if world != args.gpus and rank == 0:
         print(f'bench.py: note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
 
-    V, W = pkg('vocoder'), pkg('weights')
-    from oracle import iaf_oracle as O          # synthetic input generator only (not the thing measured)
+    V, W, IO = pkg('vocoder'), pkg('weights'), pkg('io')
     precision = V.resolve_precision(W.model_dims(hp), args.precision or hp.engine.precision)
     dims = W.model_dims(hp)
     n_total, t = int(hp.generate.batch_size), int(hp.generate.length)
-    n = n_total // world if args.workload == 'c4' else n_total      # c4 is strong-scaled, others weak
+    strong = args.workload == 'c4'
+    if strong and n_total % world:
+        raise SystemExit(f'bench.py: c4 shards {n_total} utterances evenly; --gpus {world} does not divide it')
+    n = n_total // world if strong else n_total             # c4 is strong-scaled, the others weak
+    n_job = n * world
     weights = W.init_weights(hp, seed=0)
-    model = V.PwvModel(dims, weights, precision)
-    noise_h, mel_h = O.synthetic_inputs(n, t, dims['hop'], dims['n_mels'], mel_seed=1234 + rank, noise_seed=1235 + rank)
+    model = V.PwvModel(dims, weights, precision, debug=debug)
+    noise_h, mel_h = IO.synthetic_batch(n, t, dims['hop'], dims['n_mels'], mel_seed=1234 + rank, noise_seed=1235 + rank)
     noise = torch.from_numpy(noise_h).to(dev)
     mel = torch.from_numpy(mel_h).to(dev)
     out = torch.empty((n, t), dtype=torch.float32, device=dev)
@@ -308,16 +358,43 @@ def main():
         one_step(ev0, ev1)
     barrier()
     t_end = time.time()
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in events]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    samples_per_step = n * t * world
+    samples_per_step = n_job * t
     value = samples_per_step * args.steps / (total_ms * 1e-3)
     launches_per_forward = model.last_launch_count()
     launches = launches_per_forward * args.steps
+
+    # ---- sustained leg: the same forward back to back for >= sustain_s seconds (one event pair around the loop; the
+    #      working set of a forward, >= 180 MB of activations streamed ~60 times, turns L2 over by itself)
+    sustained = None
+    t_sus0 = t_sus1 = None
+    if args.sustain_s > 0:
+        iters = max(args.steps, int(np.ceil(args.sustain_s * 1e3 / (total_ms / args.steps))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_sus0 = time.time()
+        e0.record()
+        for _ in range(iters):
+            model.forward(noise, mel, out=out)
+        e1.record()
+        barrier()
+        t_sus1 = time.time()
+        sus_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+        sus_ms = float(sus_ms.item())
+        sustained = {'value': samples_per_step * iters / (sus_ms * 1e-3), 'unit': 'samples/s', 'iterations': iters, 'seconds': sus_ms * 1e-3,
+                     'ms_per_step': sus_ms / iters, 'note': 'back-to-back forwards, no L2 flush in between, one CUDA-event pair around the loop'}
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop(t_begin, t_end)           # samples of the K timed steps
+        if sustained is not None:
+            sustained['clocks'] = window_clocks(sampler.lines, t_sus0, t_sus1)
+            launches += launches_per_forward * sustained['iterations']
 
     # ---- roofline of the dominant kernel (gated dilated layer), separate profiled steps
     pk = peaks()
@@ -337,40 +414,49 @@ def main():
     # mode 1: every launch bracketed (serialised) -> the isolated launch duration, what ncu's list shows
     layer_ms, layer_n, fwd_ms = profiled(2)
     iso_ms, iso_n, _ = profiled(1)
-    # One launch of the gated-layer kernel runs one layer of both bodies; the algorithmic bytes per launch:
-    # each body reads its 64-channel fp32 input once and writes its output once.
+    # One launch of the gated-layer kernel runs one layer of both bodies. Algorithmic bytes per launch:
+    # each body reads its 64-channel input once and writes its output once, sizeof(act) bytes per element:
+    # 4 in fp32 / f16x3 (two fp16 planes hi + lo), 2 in bf16 on the plane path (one bf16 plane).
+    planes_path = precision != 'fp32' and debug.get('path', 1) == 1
+    act_bytes = 2 if (precision == 'bf16' and planes_path) else 4
     n_gated = sum(len(d) for d in dims['dilations'])                     # gated layers per forward (x 2 bodies each)
-    bytes_per_layer = 2 * n * t * (2 * dims['R'] * 4)
+    bytes_per_layer = 2 * n * t * (2 * dims['R'] * act_bytes)
     layer_s = float(np.median(layer_ms)) * 1e-3                          # device time of all gated-layer launches
     achieved = n_gated * bytes_per_layer / layer_s / 1e9
     mac_per_layer = 2 * n * t * (2 * dims['R'] * 2 * dims['D'] + dims['D'] * dims['R'])
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            tj = json.load(fh)
-            key = precision + '_layers' if (launches_per_forward >= n_gated and precision + '_layers' in tj) else precision
-            traffic = tj.get(key, {}).get('dram_bytes_per_launch')
+    if precision == 'fp32':
+        kernel, kkey = 'k_layer_simt: gated dilated layer, fp32 FFMA, both bodies per launch', 'k_layer_simt:fp32'
+    elif planes_path:
+        kernel = ('k_layer_h: gated dilated layer on tcgen05, activations as 16-bit planes in HBM, both bodies per launch; '
+                  'one launch per layer chained by programmatic dependent launch')
+        kkey = 'k_layer_h:' + precision
+    else:
+        kernel, kkey = 'k_layer_tc / k_flow_tc (round-1 fp32-row kernels, debug path 0)', 'k_layer_tc:' + precision
+    traffic, traffic_src = measured_traffic(kkey)
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
-                'traffic': traffic, 'peak_source': pk['source'], 'kernel': ('gated dilated layers in k_flow_tc (tcgen05; one persistent launch per flow, both bodies; figures per gated layer)' if launches_per_forward < n_gated else 'gated dilated layer k_layer_tc (tcgen05, both bodies per launch; one launch per layer, programmatic dependent launch)') if precision != 'fp32' else 'gated dilated layer (fp32 FFMA, both bodies)',
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['source'], 'kernel': kernel,
                 'bytes_per_launch': n_gated * bytes_per_layer / max(layer_n, 1), 'avg_launch_us': layer_s * 1e6 / max(layer_n, 1),
                 'isolated_launch_us': float(np.median(iso_ms)) * 1e3 / max(iso_n, 1),
                 'frac_isolated': n_gated * bytes_per_layer / (float(np.median(iso_ms)) * 1e-3) / 1e9 / pk['hbm'],
                 'launches_per_step': layer_n, 'gated_layers_per_step': n_gated, 'us_per_layer': layer_s * 1e6 / n_gated,
                 'share_of_step': float(np.median(layer_ms) / np.median(fwd_ms)),
                 'tflops_fp32_equiv': 2 * n_gated * mac_per_layer / layer_s / 1e12,
-                'note': 'algorithmic bytes = 512 B per sample per body-layer (SURVEY 8d); avg_launch_us = CUDA events around each flow\'s chain of '
-                        'gated-layer launches as launched in the timed steps / launches; isolated_launch_us = every launch bracketed (serialised, what ncu lists); '
-                        'the kernel is bound by the length of the per-tile chain with two tiles resident per SM (TMEM / shared-memory capacity), no unit saturated: see DESIGN.md 7'}
+                'act_bytes_per_element': act_bytes,
+                'note': f'algorithmic bytes = {2 * dims["R"] * act_bytes} B per sample per body-layer (SURVEY 8d: sizeof(act) x 2 x R); avg_launch_us = CUDA events around '
+                        'each flow\'s chain of gated-layer launches as launched in the timed steps / launches; isolated_launch_us = every launch bracketed '
+                        '(serialised, what ncu lists)'}
 
-    # ---- e2e: host buffers in, host buffer out, copies inside the timed region.
-    #      N = 1: the C-ABI call pwv_forward_host (H2D + kernels + D2H + sync inside the call).
-    #      N > 1: rank 0 owns the whole job's pinned host batch: H2D on rank 0 -> NCCL scatter of
-    #             (noise, mel) over NVLink -> forward on every rank -> NCCL gather of wav -> D2H on rank 0
-    #             (parallel-wavenet-vocoder_b200/dist.py); timed on rank 0, max over ranks.
+    # ---- e2e: host buffers in, host buffer out, copies inside the timed region, through the C-ABI call
+    #      pwv_forward_host (H2D + kernels + D2H + sync inside the call).
+    #      N = 1: pinned host buffers of the process.
+    #      N > 1 (hostshard): ONE pinned host batch in shared memory holds the whole job; every rank runs
+    #             pwv_forward_host on its own block of utterances (its own PCIe link), rank 0 owns the complete
+    #             output after the barrier (parallel-wavenet-vocoder_b200/dist.py).
+    #      N > 1 (nccl): rank-0 H2D -> NCCL scatter -> pwv_forward per rank -> NCCL gather -> rank-0 D2H (round-1 form).
     e2e = None
     if not args.no_e2e:
         steps_e2e = max(3, min(args.steps, 10))
+        t_mel = 1 + t // dims['hop']
         if world == 1:
             pin_n = torch.from_numpy(noise_h).pin_memory()
             pin_m = torch.from_numpy(mel_h).pin_memory()
@@ -386,19 +472,38 @@ def main():
                 model.forward_host(pin_n, pin_m, pin_o)      # H2D + kernels + D2H + sync inside
                 e2e_s += time.perf_counter() - t0
             api = 'pwv_forward_host (pinned host buffers)'
-            h2d, d2h = int(noise_h.nbytes + mel_h.nbytes), int(n * t * 4)
+        elif args.e2e_mode == 'hostshard':
+            D = pkg('dist')
+            batch = D.SharedHostBatch(n_job, t, t_mel, dims['n_mels'])
+            if rank == 0:
+                noise_all, mel_all = IO.synthetic_batch(n_job, t, dims['hop'], dims['n_mels'])
+                batch.fill(noise_all, mel_all)
+            else:
+                batch.fill(None, None)
+            for _ in range(2):
+                D.hostshard_forward(model.forward_host, batch)
+            e2e_s = 0.0
+            for _ in range(steps_e2e):
+                flush.fill_(1)
+                barrier()
+                t0 = time.perf_counter()
+                D.hostshard_forward(model.forward_host, batch)    # per rank: H2D + kernels + D2H + sync; then the barrier
+                e2e_s += time.perf_counter() - t0
+            api = ('one pinned host batch in shared memory (pinned: %s); every rank: pwv_forward_host on its own shard '
+                   '(H2D + kernels + D2H + sync), barrier; rank 0 owns the whole output' % batch.pinned)
+            batch.close()
         else:
             D = pkg('dist')
-            n_all, t_mel = n * world, 1 + t // dims['hop']
             if rank == 0:
-                noise_all, mel_all = O.synthetic_inputs(n_all, t, dims['hop'], dims['n_mels'])
+                noise_all, mel_all = IO.synthetic_batch(n_job, t, dims['hop'], dims['n_mels'])
                 pin_n = torch.from_numpy(noise_all).pin_memory()
                 pin_m = torch.from_numpy(mel_all).pin_memory()
-                pin_o = torch.empty((n_all, t), dtype=torch.float32).pin_memory()
+                pin_o = torch.empty((n_job, t), dtype=torch.float32).pin_memory()
+
             def one_e2e():
                 nz = pin_n.to(dev, non_blocking=True) if rank == 0 else None
                 ml = pin_m.to(dev, non_blocking=True) if rank == 0 else None
-                full = D.sharded_forward(lambda a, b: model.forward(a, b), nz, ml, n_all, t, t_mel, dims['n_mels'], dev)
+                full = D.sharded_forward(lambda a, b: model.forward(a, b), nz, ml, n_job, t, t_mel, dims['n_mels'], dev)
                 if rank == 0:
                     pin_o.copy_(full, non_blocking=True)
                 torch.cuda.synchronize()
@@ -412,7 +517,7 @@ def main():
                 one_e2e()
                 e2e_s += time.perf_counter() - t0
             api = 'rank-0 pinned host batch -> H2D -> NCCL scatter -> pwv_forward per rank -> NCCL gather -> D2H'
-            h2d, d2h = int(n_all * t * 4 + n_all * t_mel * dims['n_mels'] * 4), int(n_all * t * 4)
+        h2d, d2h = int(n_job * t * 4 + n_job * t_mel * dims['n_mels'] * 4), int(n_job * t * 4)
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -431,17 +536,36 @@ def main():
         line = {
             'metric': 'audio_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'strong' if args.workload == 'c4' else 'weak', 'vs_baseline': None,
-            'dtype': {'fp32': 'f32', 'f16x3': 'f32 (fp16 hi/lo 3-term tensor-core split, fp32 accumulate)', 'bf16': 'bf16'}[precision],
+            'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'f16x3': 'f32 (fp16 hi/lo 3-term tensor-core split, fp32 accumulate; activations stored as fp16 hi + lo planes)',
+                      'bf16': 'bf16 (fp32 accumulate)'}[precision],
             'data': 'synthetic',
-            'config': {'workload': WORKLOADS[args.workload][1], 'per_gpu_batch': n, 'length': t, 'precision': precision,
-                       'tc_variant': os.environ.get('PWV_TC_VARIANT', 'default'),
-                       'l2': 'flushed (256 MB write) before every timed step', 'timing': 'CUDA events per step, max over ranks'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+            'config': workload_config(args.workload, hp, world),
+            'engine': {'precision': precision, 'per_gpu_batch': n, 'activation_layout': 'planes' if planes_path else 'fp32 rows', 'debug': debug},
+            'roofline': roofline, 'sustained': sustained, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }
         guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def window_clocks(lines, t_begin, t_end):
+    sm, power, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ts, line in lines:
+        parts = [p.strip() for p in line.split(',')]
+        if len(parts) < 7 or not (t_begin <= ts <= t_end + 0.1):
+            continue
+        try:
+            sm.append(float(parts[0])); power.append(float(parts[2]))
+        except ValueError:
+            continue
+        for name, flag in zip(names, parts[3:7]):
+            if flag.lower().startswith('active'):
+                reasons.add(name)
+    if not sm:
+        return {'sm_mhz': None, 'samples': 0, 'reasons': []}
+    return {'sm_mhz': float(np.median(sm)), 'sm_mhz_min': float(min(sm)), 'samples': len(sm), 'power_w_max': float(max(power)), 'reasons': sorted(reasons)}
 
 
 if __name__ == '__main__':

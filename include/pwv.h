@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PWV_VERSION 101          /* major*10000 + minor*100 + patch */
+#define PWV_VERSION 200          /* major*10000 + minor*100 + patch */
 #define PWV_MAX_FLOWS 8
 #define PWV_MAX_LAYERS 64
 #define PWV_MAX_UPSAMPLE 4
@@ -144,6 +144,10 @@ int pwv_set_profiling(pwv_model* m, int enable);
  * layers of a forward from 0 with the flows concatenated (default hparams: 0..59). */
 int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int layer_index);
 int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double* forward_ms);
+/* Debug / A-B switches for tests and measurement tools (the library never reads the environment): key one of
+ * "path" (1 = 16-bit activation planes, the default; 0 = the round-1 fp32-row kernels), "pdl", "tile_flags", "flow",
+ * "seg", "rotate", "stagger", "variant", "trace_flow" -- see csrc/pwv_api.cu. Unknown keys fail with PWV_EINVAL. */
+int pwv_debug_set(pwv_model* m, const char* key, int value);
 
 #ifdef __cplusplus
 }

@@ -298,6 +298,9 @@ def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dty
         p = f'{ROOT}/iaf{i}'
         scale = wavenet(x, cond, W, p + '/scalar', dil, use_biases, use_skip_connection, taps)
         shift = wavenet(x, cond, W, p + '/shifter', dil, use_biases, use_skip_connection, taps)
+        if taps is not None:                                                 # the two WaveNet outputs (modules.py:56-57)
+            taps[p + '/scalar'] = _OPS.to_numpy(scale[:, :, 0]).copy()
+            taps[p + '/shifter'] = _OPS.to_numpy(shift[:, :, 0]).copy()
         x = x * scale + shift                                                # modules.py:57-59
         x = normalize(x, W, f'{ROOT}/normalize{i}')                          # models.py:70
         if taps is not None:

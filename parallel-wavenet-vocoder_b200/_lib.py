@@ -20,7 +20,7 @@ EXPORTS = (
     'pwv_version', 'pwv_last_error', 'pwv_device_count', 'pwv_model_create', 'pwv_model_destroy',
     'pwv_model_num_variables', 'pwv_model_variable', 'pwv_model_load_weight', 'pwv_model_finalize',
     'pwv_workspace_bytes', 'pwv_forward', 'pwv_forward_host', 'pwv_last_launch_count',
-    'pwv_set_profiling', 'pwv_profile_read', 'pwv_debug_set_trace',
+    'pwv_set_profiling', 'pwv_profile_read', 'pwv_debug_set_trace', 'pwv_debug_set',
 )
 
 
@@ -84,6 +84,7 @@ def load():
     lib.pwv_last_launch_count.argtypes = [c.c_void_p]
     lib.pwv_set_profiling.argtypes = [c.c_void_p, c.c_int]
     lib.pwv_debug_set_trace.argtypes = [c.c_void_p, c.c_void_p, c.c_int]
+    lib.pwv_debug_set.argtypes = [c.c_void_p, c.c_char_p, c.c_int]
     lib.pwv_profile_read.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_int), c.POINTER(c.c_double)]
     for name in EXPORTS:
         if name not in ('pwv_last_error',):

@@ -17,6 +17,7 @@
 
 #include "pwv_simt.cuh"
 #include "pwv_tc.cuh"
+#include "pwv_tc2.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -101,14 +102,16 @@ struct pwv_model {
 
   // profiling (pwv_set_profiling): event pairs around the gated-layer launches of the last forward
   long long* trace = nullptr;    // pwv_debug_set_trace
-  bool use_pdl = true;           // PWV_NO_PDL=1 in the environment switches it off (debugging)
-  bool use_flags = true;         // tile handshake between consecutive gated layers (PWV_NO_TILE_FLAGS=1: off)
-  int tc_stagger = 0;            // PWV_TC_STAGGER (A/B runs): how far slot 1 starts behind slot 0 in k_flow_tc
-  bool use_flow = true;          // one persistent launch per flow (k_flow_tc); PWV_TC_FLOW=0: one launch per layer
-  bool tc_rotate = false;        // k_flow_tc: tile-to-CTA assignment rotates from layer to layer (PWV_TC_ROTATE=1; A/B switch)
-  int tc_seg = 0;                // k_flow_tc: gated layers per launch (PWV_TC_SEG; 0 = by job size, see launch_layers_tc)
-  bool tc_quiet = false;         // EXPERIMENTAL (PWV_TC_QUIET=1): 512-thread form of k_flow_tc, helper work folded into the slots' head warps
-  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // PWV_TC_VARIANT=0|1 in the environment overrides (A/B runs)
+  // Debug / A-B switches, settable only through pwv_debug_set (tests, tools); the product path never reads the environment.
+  bool use_pdl = true;           // "pdl": programmatic dependent launch between the gated-layer launches
+  bool use_flags = true;         // "tile_flags": tile handshake between consecutive gated layers
+  int tc_path = 1;               // "path": 1 = 16-bit activation planes (k_layer_h, round 2), 0 = fp32 rows (k_layer_tc / k_flow_tc, round 1)
+  int tc_stagger = 0;            // "stagger": how far slot 1 starts behind slot 0 in k_flow_tc
+  bool use_flow = true;          // "flow" (path 0): one persistent launch per flow (k_flow_tc) inside its job-size window
+  bool tc_rotate = false;        // "rotate" (path 0): k_flow_tc tile-to-CTA assignment rotates from layer to layer
+  int tc_seg = 0;                // "seg" (path 0): k_flow_tc gated layers per launch (0 = by job size)
+  int tc_variant = PWV_TC_VARIANT_DEFAULT;   // "variant": 0 scalar epilogue arithmetic, 1 packed fp32x2, 2 (path 0) setmaxnreg register re-partition
+  bool trace_flow = false;       // "trace_flow" (path 0): the phase trace follows k_flow_tc instead of forcing per-layer launches
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
                                  // 2: one pair around each flow's chain of gated-layer launches (as in production)
@@ -213,8 +216,18 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
-    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_tc<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TC_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_flow_tc<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCF_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -251,8 +264,6 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
     return fail(PWV_EINVAL, "skip_channels (%d) must equal 2*residual_channels (%d)", hp->skip_channels, 2 * hp->residual_channels);
   const int C = hp->residual_channels;
   if (C != 64 && C != 128 && C != 256) return fail(PWV_EINVAL, "residual_channels=%d: supported 64, 128, 256", C);
-  if (hp->use_skip_connection && hp->precision != PWV_PREC_FP32)
-    return fail(PWV_EINVAL, "use_skip_connection=True is implemented on the fp32 path only (precision fp32), not on the tensor-core kernels");
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
   if (hp->cond_upsample != PWV_UPSAMPLE_REPEAT && hp->cond_upsample != PWV_UPSAMPLE_TRANSPOSED_CONV)
@@ -287,17 +298,6 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   m->Cc = hp->condition_channels;
   m->total_layers = total;
   m->max_layers = mx;
-  m->use_pdl = getenv("PWV_NO_PDL") == nullptr;
-  m->use_flags = getenv("PWV_NO_TILE_FLAGS") == nullptr && m->use_pdl;
-  if (const char* v = getenv("PWV_TC_FLOW")) m->use_flow = atoi(v) != 0;
-  if (const char* v = getenv("PWV_TC_STAGGER")) m->tc_stagger = atoi(v);
-  if (const char* v = getenv("PWV_TC_QUIET")) m->tc_quiet = atoi(v) != 0;
-  if (const char* v = getenv("PWV_TC_ROTATE")) m->tc_rotate = atoi(v) != 0;
-  if (const char* v = getenv("PWV_TC_SEG")) m->tc_seg = atoi(v);
-  if (const char* v = getenv("PWV_TC_VARIANT")) {
-    const int k = atoi(v);
-    if (k >= 0 && k <= 1) m->tc_variant = k;
-  }
   build_var_list(m);
   *out = m;
   return PWV_OK;
@@ -711,6 +711,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   // (DESIGN.md 4.1): all 16 worker warps serving both slots in a static phase order, and a 1024-thread kernel.
   auto kern = bf16 ? pwv::k_layer_tc<true, false> : pwv::k_layer_tc<false, true>;
   if (m->tc_variant == 1) kern = bf16 ? pwv::k_layer_tc<true, false, true> : pwv::k_layer_tc<false, true, true>;
+  if (m->tc_variant == 2) kern = bf16 ? pwv::k_layer_tc<true, false, false, true> : pwv::k_layer_tc<false, true, false, true>;
   const int block = pwv::TC_THREADS;
   const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
   const int tiles_body = N * tiles_per_utt;
@@ -732,7 +733,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   // PWV_TC_SEG = n forces k_flow_tc with n layers per launch (>= L: the whole flow).
   const double tiles_per_cta = (double)tiles_body / (grid / 2);
   const bool in_window = tiles_per_cta >= 2.5 && tiles_per_cta <= 17.0;
-  const bool flow_kernel = m->use_flow && m->use_flags && m->tc_variant == 0 && m->profiling != 1 && !tap_layer && (!m->trace || getenv("PWV_TRACE_FLOW")) &&
+  const bool flow_kernel = m->use_flow && m->use_flags && (m->tc_variant == 0 || m->tc_variant == 2) && m->profiling != 1 && !tap_layer && (!m->trace || m->trace_flow) &&
                            L <= pwv::TCF_MAX_LAYERS && grid <= m->num_sms && (m->tc_seg > 0 || (in_window && c_hop > 1));
   // (c_hop == 1: full-rate conditioning rows, cond_upsample_method 'transposed_conv' -- read from global memory per row;
   //  that combination is verified on the per-layer kernels only)
@@ -759,7 +760,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       if (m->profiling == 2 && l0 == 0) PWV_PROF_MARK(m, st);
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(pwv::tcf_threads(m->tc_quiet));
+      cfg.blockDim = dim3(pwv::tcf_threads(false));
       cfg.dynamicSmemBytes = pwv::TCF_SMEM_BYTES;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
@@ -767,9 +768,9 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = m->use_pdl ? 1 : 0;
-      if (m->tc_quiet) {
-        if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, true>, maps[0], maps[1], q));
-        else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, true>, maps[0], maps[1], q));
+      if (m->tc_variant == 2) {
+        if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false, false, false, true>, maps[0], maps[1], q));
+        else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true, false, false, true>, maps[0], maps[1], q));
       } else if (bf16) PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<true, false>, maps[0], maps[1], q));
       else PWV_CUDA(cudaLaunchKernelEx(&cfg, pwv::k_flow_tc<false, true>, maps[0], maps[1], q));
       if (m->profiling == 2 && l0 + Ls == L) PWV_PROF_MARK(m, st);
@@ -835,6 +836,160 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
   return PWV_OK;
 }
 
+
+// 3-D TMA map of an activation buffer in the plane layout [planes * 2N utterance-bodies][T][64] 16-bit (fp16 hi / lo
+// planes, or one bf16 plane): box = 64 channels x 128 rows x 1 (16 KB), 128B swizzle, zero OOB fill.
+static int encode_plane_map(CUtensorMap* map, void* base, int N, int T, int planes, bool bf16) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PWV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PWV_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)planes * 2 * N};
+  const cuuint64_t strides[2] = {64 * 2, (cuuint64_t)T * 64 * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)pwv::TC_TM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PWV_ECUDA, "cuTensorMapEncodeTiled (planes) failed with CUresult %d (N=%d, T=%d)", (int)r, N, T);
+  return PWV_OK;
+}
+
+template <bool BF16, bool LAST>
+static cudaError_t launch_layer_h(const cudaLaunchConfig_t* cfg, bool pk, const CUtensorMap& in, const CUtensorMap& out, const pwv::ThLayerParams& p) {
+  if (pk) return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, true>, in, out, p);
+  return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, false>, in, out, p);
+}
+
+// gated layers and post-net of one flow on the tensor cores, activations as 16-bit planes (k_layer_h, pwv_tc2.cuh):
+// one launch per gated layer, chained by programmatic dependent launch (+ the per-tile flag handshake inside the
+// job-size window where it pays); the flow's last layer writes z as fp32 rows for k_post_tc.
+//   maps_h[b] = plane map of act[b], maps_f[b] = fp32 row map of act[b]
+static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* maps_h, const CUtensorMap* maps_f, int flow, int N, int T,
+                           cudaStream_t st, const pwv_taps* taps, int* cur_buf, int* launches) {
+  constexpr int C = pwv::TC_C;
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], t_mel = cond_rows(m, T), c_hop = cond_hop(m);
+  const bool bf16 = hp.precision == PWV_PREC_BF16;
+  const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
+  const int tiles_body = N * tiles_per_utt;
+  int grid = 2 * tiles_body < m->num_sms ? 2 * tiles_body : m->num_sms;
+  grid &= ~1;
+  if (grid < 2) grid = 2;
+  size_t layer_base = 0;
+  for (int i = 0; i < flow; ++i) layer_base += 2 * (size_t)hp.n_layers[i];
+  int cur = *cur_buf;
+  // Tile flags between consecutive layers let a layer's tiles start while the previous layer's tail is still running;
+  // they pay while a CTA owns few tiles per layer (round-1 sweep: 2.5 .. 17), beyond that the whole-kernel wait of the
+  // programmatic dependent launch costs less than the flag traffic.
+  const double tiles_per_cta = (double)tiles_body / (grid / 2);
+  // (use_skip_connection puts a skip-sum kernel between consecutive layers: no tile handshake across it)
+  const bool layer_flags = m->use_flags && m->use_pdl && m->profiling != 1 && !hp.use_skip_connection && tiles_per_cta >= 1.5 && tiles_per_cta <= 17.0;
+  const size_t plane_elems = (size_t)2 * N * T * C;
+  using SCfg = pwv::TileCfg<64>;
+  const dim3 sgrid((T + SCfg::TM - 1) / SCfg::TM, N, 2);
+  for (int j = 0; j < L; ++j) {
+    const bool last = j == L - 1;
+    pwv::ThLayerParams p;
+    for (int b = 0; b < 2; ++b) {
+      p.image[b] = m->tc.d_images + (layer_base + (size_t)b * L + j) * pwv::TC_IMAGE_BYTES;
+      p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
+    }
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = c_hop; p.dilation = hp.dilations[flow][j];
+    p.tiles_per_utt = tiles_per_utt;
+    p.cb_in_smem = ((pwv::TC_TM - 1) / c_hop + 2 <= pwv::TC_CB_FRAMES) ? 1 : 0;
+    int* fl = w.flags + (layer_base / 2 + (size_t)j) * 2 * tiles_body;
+    p.flags_out = (layer_flags && j + 1 < L) ? fl : nullptr;
+    p.flags_in = (layer_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
+    p.prev_dilation = j > 0 ? hp.dilations[flow][j - 1] : 0;
+    p.z_out = (hp.use_skip_connection && !last) ? w.zbuf : nullptr;
+    p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
+    if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(pwv::TC_THREADS);
+      cfg.dynamicSmemBytes = pwv::TH_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = (m->profiling == 1 || !m->use_pdl) ? 0 : 1;
+      const bool pk = m->tc_variant == 1;
+      const CUtensorMap& in = maps_h[cur];
+      const CUtensorMap& out = last ? maps_f[cur ^ 1] : maps_h[cur ^ 1];
+      cudaError_t e;
+      if (bf16) e = last ? launch_layer_h<true, true>(&cfg, pk, in, out, p) : launch_layer_h<true, false>(&cfg, pk, in, out, p);
+      else e = last ? launch_layer_h<false, true>(&cfg, pk, in, out, p) : launch_layer_h<false, false>(&cfg, pk, in, out, p);
+      PWV_CUDA(e);
+    }
+    if (m->profiling == 1 || (m->profiling == 2 && last)) PWV_PROF_MARK(m, st);
+    if (m->profiling) ++m->prof_launches;
+    ++*launches;
+    cur ^= 1;
+    if (hp.use_skip_connection) {     // skip_sum (+)= z_j . Ws_j + bs_j in layer order (reference modules.py:147), exact fp32 FFMA kernel
+      pwv::SkipParams sp;
+      sp.z = last ? w.act[cur] : w.zbuf;
+      for (int b = 0; b < 2; ++b) {
+        const LayerOff& lo = m->bodies[flow * 2 + b].layers[j];
+        sp.ws[b] = m->d_arena + lo.ws;
+        sp.bs[b] = m->d_arena + lo.bs;
+      }
+      sp.skip_sum = w.skip; sp.N = N; sp.T = T; sp.first = j == 0 ? 1 : 0;
+      pwv::k_skip_simt<64><<<sgrid, SCfg::NT, SCfg::SMEM, st>>>(sp);
+      ++*launches;
+    }
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1)) {
+      const size_t rows = (size_t)N * T;
+      if (last) {       // (the last layer's output buffer holds z as fp32 rows)
+        PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * rows * C, sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
+      } else {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(w.act[cur]) + (size_t)taps->layer_body * rows * C;
+        const unsigned blocks = (unsigned)((rows * 32 + 255) / 256);
+        if (bf16) pwv::k_planes_to_f32<true><<<blocks, 256, 0, st>>>(src, taps->layer_out, rows, plane_elems);
+        else pwv::k_planes_to_f32<false><<<blocks, 256, 0, st>>>(src, taps->layer_out, rows, plane_elems);
+        ++*launches;
+      }
+    }
+  }
+  if (hp.use_skip_connection) {       // post-net on relu(sum of the skip outputs): the fp32 kernel
+    pwv::PostParams q;
+    q.z = w.act[cur];
+    for (int b = 0; b < 2; ++b) {
+      const BodyOff& bo = m->bodies[flow * 2 + b];
+      const LayerOff& lo = bo.layers[L - 1];
+      q.ws[b] = m->d_arena + lo.ws; q.bs[b] = m->d_arena + lo.bs;
+      q.w1[b] = m->d_arena + bo.w1; q.b1[b] = m->d_arena + bo.b1;
+      q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
+    }
+    q.y = w.ss; q.N = N; q.T = T;
+    q.skip_sum = w.skip;
+    pwv::k_post_simt<64><<<sgrid, SCfg::NT, SCfg::SMEM, st>>>(q);
+    ++*launches;
+    *cur_buf = cur;
+    PWV_CUDA(cudaGetLastError());
+    return PWV_OK;
+  }
+  PWV_CUDA(cudaMemsetAsync(w.ss, 0, sizeof(float) * 2 * (size_t)N * T, st));
+  pwv::TcPostParams q;
+  for (int b = 0; b < 2; ++b) q.image[b] = m->tc.d_post + ((size_t)flow * 2 + b) * pwv::TCP_IMAGE_BYTES;
+  q.y = w.ss; q.N = N; q.T = T; q.tiles_per_utt = tiles_per_utt;
+  if (bf16) pwv::k_post_tc<true, false><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(maps_f[cur], q);
+  else pwv::k_post_tc<false, true><<<grid, pwv::TC_THREADS, pwv::TCP_SMEM_BYTES, st>>>(maps_f[cur], q);
+  ++*launches;
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
 extern "C" {
 
 int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, void* workspace,
@@ -847,6 +1002,8 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   carve(m, N, T, (char*)workspace, &w);
   if (w.bytes > workspace_bytes) return fail(PWV_ENOMEM, "workspace has %zu bytes, %zu needed", workspace_bytes, w.bytes);
   if (((uintptr_t)workspace & 255) != 0) return fail(PWV_EINVAL, "workspace must be 256-byte aligned");
+  if (m->hp.use_skip_connection && m->hp.precision != PWV_PREC_FP32 && m->tc_path == 0)
+    return fail(PWV_EINVAL, "use_skip_connection=True is not implemented on the round-1 tensor-core kernels (debug path 0)");
   const pwv_hparams& hp = m->hp;
   const int C = m->C, Cc = m->Cc, t_mel = 1 + T / hp.hop_length;
   cudaStream_t st = (cudaStream_t)stream;
@@ -888,11 +1045,16 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     ++launches;
   }
 
-  CUtensorMap maps[2];
+  CUtensorMap maps[2], maps_h[2];
+  const bool planes = hp.precision != PWV_PREC_FP32 && m->tc_path == 1;
   if (hp.precision != PWV_PREC_FP32) {
     for (int b = 0; b < 2; ++b) {
       rc = encode_act_map(&maps[b], w.act[b], N, T);
       if (rc) return rc;
+      if (planes) {
+        rc = encode_plane_map(&maps_h[b], w.act[b], N, T, hp.precision == PWV_PREC_BF16 ? 1 : 2, hp.precision == PWV_PREC_BF16);
+        if (rc) return rc;
+      }
     }
   }
 
@@ -931,7 +1093,23 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       ++launches;
     }
     // front: IAF combine of the previous flow + causal layers
-    {
+    if (planes) {
+      pwv::FrontHParams f;
+      f.x_prev = x_prev;
+      f.scale = i == 0 ? nullptr : w.ss;
+      f.shift = i == 0 ? nullptr : w.ss + (size_t)N * T;
+      f.x_new = w.x[xcur];
+      f.wc[0] = m->d_arena + m->bodies[i * 2 + 0].causal;
+      f.wc[1] = m->d_arena + m->bodies[i * 2 + 1].causal;
+      f.act = reinterpret_cast<uint16_t*>(w.act[cur]);
+      f.N = N; f.T = T;
+      const size_t total = (size_t)N * T * (C / 8);
+      if (hp.precision == PWV_PREC_BF16) pwv::k_front_h<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      else pwv::k_front_h<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      ++launches;
+      x_prev = w.x[xcur];
+      xcur ^= 1;
+    } else {
       pwv::FrontParams f;
       f.x_prev = x_prev;
       f.scale = i == 0 ? nullptr : w.ss;
@@ -951,6 +1129,8 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       if (C == 64) rc = launch_layers_simt<64>(m, w, i, N, T, st, taps, &cur, &launches);
       else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
+    } else if (planes) {
+      rc = launch_layers_h(m, w, maps_h, maps, i, N, T, st, taps, &cur, &launches);
     } else {
       rc = launch_layers_tc(m, w, maps, i, N, T, st, taps, &cur, &launches);
     }
@@ -1012,6 +1192,22 @@ int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int launch_index
   if (!m) return fail(PWV_EINVAL, "null model");
   m->trace = device_buffer;
   m->trace_launch = launch_index;
+  return PWV_OK;
+}
+
+int pwv_debug_set(pwv_model* m, const char* key, int value) {
+  if (!m || !key) return fail(PWV_EINVAL, "null argument");
+  const std::string k(key);
+  if (k == "pdl") m->use_pdl = value != 0;
+  else if (k == "tile_flags") m->use_flags = value != 0;
+  else if (k == "path") { if (value != 0 && value != 1) return fail(PWV_EINVAL, "path must be 0 or 1"); m->tc_path = value; }
+  else if (k == "flow") m->use_flow = value != 0;
+  else if (k == "stagger") m->tc_stagger = value;
+  else if (k == "rotate") m->tc_rotate = value != 0;
+  else if (k == "seg") m->tc_seg = value;
+  else if (k == "variant") { if (value < 0 || value > 2) return fail(PWV_EINVAL, "variant must be 0, 1 or 2"); m->tc_variant = value; }
+  else if (k == "trace_flow") m->trace_flow = value != 0;
+  else return fail(PWV_EINVAL, "unknown debug switch '%s'", key);
   return PWV_OK;
 }
 

@@ -453,6 +453,14 @@ __device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_
     if (SPLIT) ptx::tmem_st8(taddr_lo + c * 8, lo);
   }
 }
+// Register re-partition between the warp roles (setmaxnreg works per warpgroup = 4 consecutive warps): the kernels
+// launch with 640 threads x 96 registers; the helper warpgroup (warps 16-19: MMA issuers, TMA producers) hands
+// registers back, the four worker warpgroups take them (512 x 120 + 128 x 32 = 65,536 = the whole register file).
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int TC_WORKER_REGS = 120, TC_HELPER_REGS = 32;
 constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
 constexpr int TC_MMA_WARP = 16;                           // 16, 17: MMA issuer of tile slot 0, 1
 constexpr int TC_TMA_WARP = 18;                           // 18, 19: TMA producer of tile slot 0, 1
@@ -488,7 +496,7 @@ __device__ __forceinline__ void tc_unlock(int* lock) {
 
 // PK: packed fp32x2 epilogue arithmetic (bit-identical results, ~15 % fewer worker instructions, same speed:
 // the worker phases are latency-bound, not issue-bound -- kept selectable for A/B runs).
-template <bool BF16, bool SPLIT, bool PK = false>
+template <bool BF16, bool SPLIT, bool PK = false, bool RG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
   using namespace ptx;
@@ -529,7 +537,11 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1) {
+  // (RG: each role's code sits inside its own branch after the setmaxnreg -- code after a merge of the helper and worker
+  //  paths would be allocated with the smaller of the two budgets)
+  if (warp >= TC_MMA_WARP) {
+   if (RG) reg_dec<TC_HELPER_REGS>();
+   if (warp < TC_TMA_WARP) {
     // ======================= MMA issuers (one per tile slot); the first also loads the weights =======================
     if (elect_one()) {
       const int s = warp - TC_MMA_WARP;
@@ -594,7 +606,7 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
       }
     }
     __syncwarp();
-  } else if (warp >= TC_TMA_WARP) {
+   } else {
     // ======================= TMA producers (one per tile slot): boxes in, output boxes out =======================
     if (elect_one()) {
       const int s = warp - TC_TMA_WARP;
@@ -693,7 +705,9 @@ k_layer_tc(const __grid_constant__ CUtensorMap map_in, TcLayerParams p) {
       }
     }
     __syncwarp();
+   }
   } else {
+    if (RG) reg_inc<TC_WORKER_REGS>();
     // ======================= workers: operand prep, epilogues =======================
     // warp -> (tile slot, channel half, lane quarter); thread -> (row of the tile, 32 of the 64 channels)
     const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
@@ -919,7 +933,7 @@ struct TcFlowBarriers {
 constexpr int TCF_NB_AREADY = 1, TCF_NB_ZREADY = 3, TCF_NB_D1 = 5, TCF_NB_D2 = 7, TCF_NB_YFREE = 9;
 constexpr int TCF_NB_COUNT = 256;              // the slot's 8 worker warps
 
-template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false>
+template <bool BF16, bool SPLIT, bool PK = false, bool QUIET = false, bool RG = false>
 __global__ void __launch_bounds__(tcf_threads(QUIET), 1)
 k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const __grid_constant__ TcFlowParams p) {
   using namespace ptx;
@@ -1105,7 +1119,9 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
   tc_fence_after_sync();
   const uint32_t tmem = bars->tmem_base;
 
-  if (!QUIET && (warp == TC_MMA_WARP || warp == TC_MMA_WARP + 1)) {
+  if (!QUIET && warp >= TC_MMA_WARP) {
+   if (RG) reg_dec<TC_HELPER_REGS>();
+   if (warp < TC_TMA_WARP) {
     // ======================= MMA issuers (one per tile slot), polled form; slot 0's also hands the weights over =======================
     if (elect_one() && n_local > 0) {
       const int s = warp - TC_MMA_WARP;
@@ -1135,7 +1151,7 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       }
     }
     __syncwarp();
-  } else if (!QUIET && warp >= TC_TMA_WARP) {
+   } else {
     // ======================= TMA producers (one per tile slot), polled form =======================
     if (elect_one()) {
       const int s = warp - TC_TMA_WARP;
@@ -1187,7 +1203,9 @@ k_flow_tc(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUte
       }
     }
     __syncwarp();
+   }
   } else {
+    if (RG && !QUIET) reg_inc<TC_WORKER_REGS>();
     // ======================= workers: operand prep, epilogues =======================
     const int slot = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int r = quarter * 32 + lane;

@@ -1,12 +1,25 @@
 """Utterance sharding across the GPUs of one box.
 
 The path has no exchange step: every utterance is independent, weights (19.4 MB) are
-replicated. One process per GPU (torchrun); NCCL moves only inputs and outputs:
-rank `src` scatters `(noise[N,T], mel[N,t_mel,n_mels])` in contiguous blocks of utterances and
-gathers `wav[N,T]` (~12 bytes per audio sample in total). Uneven splits are supported (the first
-`N % world` ranks take one more utterance). Works with any backend (`nccl` on GPUs, `gloo` in the
-CPU tests) because it only uses point-to-point `send/recv` via `batch_isend_irecv`.
+replicated. One process per GPU (torchrun). Two ways of moving the inputs / outputs (~12 bytes per
+audio sample in total) between the job's host batch and the ranks:
+
+* `SharedHostBatch` (default of bench.py's e2e leg): the whole job's `(noise, mel, wav)` lives in ONE
+  host buffer in POSIX shared memory that every rank maps and pins (cudaHostRegister). Each rank copies
+  its own contiguous block of utterances host->device over its OWN PCIe link, runs the forward and
+  copies its block of `wav` back into the shared buffer -- 8 links in parallel, nothing funnelled through
+  rank 0 (round 1's scatter/gather form lost 37 % at 8 GPUs to exactly that funnel: one H2D of the whole
+  batch, 21 point-to-point ops, one D2H). The only collective left is the barrier that tells rank 0 the
+  output is complete.
+* `scatter_inputs` / `gather_outputs`: rank `src` holds the batch on ITS device and NCCL moves the
+  shards over NVLink (grouped `send/recv`, one `batch_isend_irecv` per direction). Kept for callers whose
+  batch is already device-resident on one rank; works with `gloo` too (CPU tests).
+
+Uneven splits are supported (the first `N % world` ranks take one more utterance).
 """
+import os
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -77,3 +90,80 @@ def sharded_forward(forward, noise, mel, n_total, t, t_mel, n_mels, device, src=
     else:
         wav_s = torch.empty((0, t), dtype=torch.float32, device=device)
     return gather_outputs(wav_s, n_total, src, group)
+
+
+class SharedHostBatch:
+    """The job's host batch in POSIX shared memory, mapped by every rank of the node.
+
+    Layout (float32): noise [N][T] | mel [N][t_mel][n_mels] | wav [N][T]. Rank `src` creates and fills it,
+    the others map it after a barrier; with `pin=True` every rank page-locks its mapping so that the
+    copies to and from its GPU are real asynchronous DMA transfers. `shard()` returns this rank's views.
+    """
+
+    def __init__(self, n_total, t, t_mel, n_mels, name=None, src=0, group=None, pin=True, directory='/dev/shm'):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_total, self.t, self.t_mel, self.n_mels = int(n_total), int(t), int(t_mel), int(n_mels)
+        self.src, self.group = src, group
+        sizes = [self.n_total * self.t, self.n_total * self.t_mel * self.n_mels, self.n_total * self.t]
+        self._offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        total = int(self._offsets[-1])
+        if name is None:
+            name = 'pwv_batch_%s_%s' % (os.environ.get('MASTER_PORT', '0'), os.environ.get('TORCHELASTIC_RUN_ID', 'x'))
+        self.path = os.path.join(directory, name)
+        if self.rank == src:
+            with open(self.path, 'wb') as fh:
+                fh.truncate(total * 4)
+        dist.barrier(group)
+        self.buf = torch.from_file(self.path, shared=True, size=total, dtype=torch.float32)
+        self.pinned = False
+        if pin and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), total * 4, 0)
+            self.pinned = int(rc) == 0
+        self.bounds = shard_bounds(self.n_total, self.world)
+        dist.barrier(group)
+        if self.rank == src:                       # every rank has the file open: unlink the name now
+            os.unlink(self.path)
+
+    def _view(self, i, shape):
+        a, b = int(self._offsets[i]), int(self._offsets[i + 1])
+        return self.buf[a:b].view(*shape)
+
+    @property
+    def noise(self):
+        return self._view(0, (self.n_total, self.t))
+
+    @property
+    def mel(self):
+        return self._view(1, (self.n_total, self.t_mel, self.n_mels))
+
+    @property
+    def wav(self):
+        return self._view(2, (self.n_total, self.t))
+
+    def fill(self, noise, mel):
+        """Rank `src` writes the job's inputs; everyone returns after they are visible to all ranks."""
+        if self.rank == self.src:
+            self.noise.copy_(torch.as_tensor(noise))
+            self.mel.copy_(torch.as_tensor(mel))
+        dist.barrier(self.group)
+
+    def shard(self):
+        """-> (noise, mel, wav) host views of this rank's utterances (contiguous, pinned if `pinned`)."""
+        lo, hi = self.bounds[self.rank]
+        return self.noise[lo:hi], self.mel[lo:hi], self.wav[lo:hi]
+
+    def close(self):
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.buf.data_ptr())
+            self.pinned = False
+
+
+def hostshard_forward(forward_host, batch):
+    """Every rank runs `forward_host(noise_view, mel_view, wav_view)` (host buffers in, host buffer out -- the
+    C-ABI call pwv_forward_host) on its own shard of the shared host batch; after the barrier rank `src` holds
+    the whole job's output in `batch.wav`."""
+    noise, mel, wav = batch.shard()
+    if noise.shape[0]:
+        forward_host(noise, mel, wav)
+    dist.barrier(batch.group)
+    return batch.wav if batch.rank == batch.src else None

@@ -19,6 +19,14 @@ import torch
 from .hparam import hparam as hp
 
 
+def synthetic_batch(n, t, hop, n_mels, mel_seed=1234, noise_seed=1235):
+    """SURVEY 8(d) synthetic inputs: mel ~ U(-1, 1) (the range reference audio.py:278-286 normalises to) and the
+    logistic sample log(u) - log1p(-u) the reference draws in-graph (models.py:32-33). -> (noise (n,t), mel (n,1+t//hop,n_mels)) f32"""
+    mel = np.random.RandomState(mel_seed).uniform(-1.0, 1.0, size=(n, 1 + t // hop, n_mels))
+    u = np.random.RandomState(noise_seed).uniform(1e-7, 1.0 - 1e-7, size=(n, t))
+    return (np.log(u) - np.log1p(-u)).astype(np.float32), mel.astype(np.float32)
+
+
 class GenerationData:
     def __init__(self, data_path, batch_size, length):
         self.batch_size = int(batch_size)
@@ -39,9 +47,7 @@ class GenerationData:
         n, t = self.batch_size, self.length
         if self.synthetic:
             engine = hp.get('engine', {}) or {}
-            mel = np.random.RandomState(1234).uniform(-1, 1, size=(n, 1 + t // hop, n_mels)).astype(np.float32)
-            u = np.random.RandomState(int(engine.get('noise_seed', 1235))).uniform(1e-7, 1 - 1e-7, size=(n, t))
-            noise = (np.log(u) - np.log1p(-u)).astype(np.float32)
+            noise, mel = synthetic_batch(n, t, hop, n_mels, 1234, int(engine.get('noise_seed', 1235)))
             return None, mel, noise
         from . import melspec
         if not self.wav_files:

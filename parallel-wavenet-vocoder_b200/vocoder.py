@@ -35,19 +35,29 @@ def _assert_supported(hp):
         raise AssertionError(f'prod({strides}) != hop_length {hp.signal.hop_length} (reference models.py:106)')
 
 
+def tensor_core_covers(dims):
+    """Channel counts the tcgen05 kernels implement (csrc/pwv_tc2.cuh): R = D = 64, S = 128."""
+    return dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128
+
+
 def resolve_precision(dims, precision):
-    """'auto' -> 'f16x3' (tcgen05, fp32-level parity) when the tensor-core kernels cover the graph
-    (R = D = 64, S = 128, no skip connections), else the exact fp32 FFMA kernels."""
+    """'auto' -> 'f16x3' (tcgen05, fp32-level parity) when the tensor-core kernels cover the graph, else the exact
+    fp32 FFMA kernels -- said out loud, never silently (a user asking for 'auto' at 128 channels is told what runs)."""
     if precision in (None, '', 'auto'):
-        tc_ok = dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128 and not dims['use_skip']
-        return 'f16x3' if tc_ok else 'fp32'
+        if tensor_core_covers(dims):
+            return 'f16x3'
+        import warnings
+        warnings.warn(f"engine.precision 'auto': residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} are outside the "
+                      f"tensor-core kernels' coverage (64/64/128); running the exact fp32 FFMA kernels", RuntimeWarning, stacklevel=2)
+        return 'fp32'
     return precision
 
 
 class PwvModel:
     """Thin RAII wrapper over a finalized `pwv_model`."""
 
-    def __init__(self, dims, weights, precision='auto'):
+    def __init__(self, dims, weights, precision='auto', debug=None):
+        """`debug`: {switch: int} passed to pwv_debug_set (tests and measurement tools only; include/pwv.h)."""
         self.lib = _lib.load()
         self.dims = dims
         precision = resolve_precision(dims, precision)
@@ -55,6 +65,8 @@ class PwvModel:
         self._h = ctypes.c_void_p()
         hparams = _lib.make_hparams(dims, precision)
         _lib.check(self.lib.pwv_model_create(ctypes.byref(hparams), ctypes.byref(self._h)))
+        for key, value in (debug or {}).items():
+            _lib.check(self.lib.pwv_debug_set(self._h, key.encode(), int(value)))
         n = _lib.check(self.lib.pwv_model_num_variables(self._h))
         name = ctypes.c_char_p()
         shape = (ctypes.c_int64 * 4)()

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(L.EXPORTS) == declared
-    assert lib.pwv_version() == 101
+    assert lib.pwv_version() == 200
 
 
 def test_hparams_struct_matches_header():
@@ -64,12 +64,12 @@ def test_model_create_validates(hp):
     _, _, rc = _create(hp)
     assert rc == -1 and b'filter_width' in lib.pwv_last_error()
     hp.model.filter_width = 2
-    hp.model.use_skip_connection = True                 # fp32 path only
-    _, h2, rc = _create(hp, 'fp32')
-    assert rc == 0
-    lib.pwv_model_destroy(h2)
-    _, _, rc = _create(hp, 'f16x3')
-    assert rc == -1 and b'use_skip_connection' in lib.pwv_last_error()
+    hp.model.use_skip_connection = True                 # accepted by the fp32 and the tensor-core (plane) paths
+    for prec in ('fp32', 'f16x3'):
+        _, h2, rc = _create(hp, prec)
+        assert rc == 0
+        assert lib.pwv_debug_set(h2, b'path', 0) == 0 and lib.pwv_debug_set(h2, b'no_such_switch', 1) == -1
+        lib.pwv_model_destroy(h2)
     hp.model.use_skip_connection = False
     hp.model.residual_channels = 48
     _, _, rc = _create(hp)

@@ -11,23 +11,30 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _run(hp, weights, noise, mel, taps=None, precision=None):
+LEGACY = {'path': 0}      # the round-1 fp32-row tensor-core kernels (k_layer_tc / k_flow_tc), kept behind pwv_debug_set
+
+
+def _run(hp, weights, noise, mel, taps=None, precision=None, debug=None):
     V = pkg('vocoder')
     W = pkg('weights')
-    model = V.PwvModel(W.model_dims(hp), weights, precision or hp.engine.precision)
+    model = V.PwvModel(W.model_dims(hp), weights, precision or hp.engine.precision, debug=debug)
     out = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda(), taps=taps)
     torch.cuda.synchronize()
     return out, model
 
 
-def _oracle(hp, weights, noise, mel, taps=None):
+def _oracle(hp, weights, noise, mel, taps=None, fast=False):
+    """float64 ground truth; `fast`: the same restatement on torch's threaded CPU kernels (full-size cases)."""
     d = pkg('weights').model_dims(hp)
-    return O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], d['use_biases'], False,
-                                 dtype=np.float64, taps=taps)
+    return O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], d['use_biases'], bool(d['use_skip']),
+                                 dtype=np.float64, taps=taps, ops=O.TorchOps() if fast else None)
 
 
-@pytest.mark.parametrize('channels,precision', [(64, 'fp32'), (128, 'fp32'), (256, 'fp32'), (64, 'f16x3')])
-def test_small_against_oracle_with_taps(hp, channels, precision):
+@pytest.mark.parametrize('channels,precision,debug', [(64, 'fp32', None), (128, 'fp32', None), (256, 'fp32', None), (64, 'f16x3', None),
+                                                      (64, 'f16x3', LEGACY)])
+def test_small_against_oracle_with_taps(hp, channels, precision, debug):
+    """Every debug tap against the oracle's: a gated layer's dense output, both WaveNet outputs of every flow
+    (scale, shift: reference modules.py:56-57), x after every flow, the waveform."""
     small_case(hp, channels=channels, t=1600 if channels == 64 else 800, precision=precision)
     W = pkg('weights')
     weights = W.init_weights(hp, seed=3, bias_std=0.1)
@@ -35,13 +42,49 @@ def test_small_against_oracle_with_taps(hp, channels, precision):
     noise, mel = O.synthetic_inputs(n, t, 80, 80)
     taps = {}
     ref = _oracle(hp, weights, noise, mel, taps)
-    (out, cap), _ = _run(hp, weights, noise, mel, taps={'flow_out': True, 'scale_shift': True, 'layer': (0, 1, 2)})
+    (out, cap), _ = _run(hp, weights, noise, mel, taps={'flow_out': True, 'scale_shift': True, 'layer': (0, 1, 2)}, debug=debug)
     got_layer = cap['layer_out'].cpu().numpy()
     want_layer = taps['iaf_vocoder/iaf0/shifter/dilated_stack/layer2']
     assert np.abs(got_layer - want_layer).max() <= TOL
+    ss = cap['scale_shift'].cpu().numpy()
     for i in range(len(hp.model.dilations)):
+        assert np.abs(ss[i, 0] - taps[f'iaf_vocoder/iaf{i}/scalar']).max() <= TOL, i
+        assert np.abs(ss[i, 1] - taps[f'iaf_vocoder/iaf{i}/shifter']).max() <= TOL, i
         assert np.abs(cap['flow_out'][i].cpu().numpy() - taps[f'iaf_vocoder/iaf{i}']).max() <= TOL, i
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('precision', ['f16x3', 'fp32'])
+def test_c2_size_against_oracle(hp, precision):
+    """BASELINE config c2 ITSELF (N=8, T=16000, default hparams): every one of the 128,000 samples within 1e-4 of the
+    float64 oracle (the oracle runs on torch's threaded CPU kernels here: same restatement, ~40 s)."""
+    hp.set_hparam_yaml('bench/c2')
+    weights = pkg('weights').init_weights(hp, seed=0, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(8, 16000, 80, 80)
+    ref = _oracle(hp, weights, noise, mel, fast=True)
+    out, _ = _run(hp, weights, noise, mel, precision=precision)
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(precision, 'c2 max|delta| =', err)
+    assert err <= TOL
+
+
+@pytest.mark.timeout(900)
+def test_c4_shard_against_oracle(hp):
+    """One GPU's shard of BASELINE config c4 (32 of the 256 utterances x 16000 samples) through the f16x3 path; the
+    oracle checks utterances 0, 13 and 31 of the shard (utterances are independent: bit-exact batch independence is
+    tested separately), every sample within 1e-4."""
+    hp.set_hparam_yaml('bench/c4')
+    weights = pkg('weights').init_weights(hp, seed=0, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(32, 16000, 80, 80, mel_seed=77, noise_seed=78)
+    out, _ = _run(hp, weights, noise, mel, precision='f16x3')
+    out = out.cpu().numpy()
+    assert np.isfinite(out).all()
+    pick = [0, 13, 31]
+    ref = _oracle(hp, weights, noise[pick], mel[pick], fast=True)
+    err = np.abs(out[pick] - ref).max()
+    print('c4 shard max|delta| =', err)
+    assert err <= TOL
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
@@ -85,10 +128,11 @@ def test_edge_shapes(hp, n, t, precision):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_tran.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz'])
 def test_golden_fixture(hp, name, precision):
     """Committed fixtures produced by executing the reference's own modules.py/models.py under the
-    numpy TF stand-in (tests/golden/make_golden_from_reference.py)."""
+    numpy TF stand-in (tests/golden/make_golden_from_reference.py): pinned to the reference's graph code, not to
+    TensorFlow's kernels."""
     from conftest import load_golden
     weights, noise, mel, wav, _ = load_golden(hp, name)
     out, _ = _run(hp, weights, noise, mel, precision=precision)
@@ -172,8 +216,15 @@ def test_bf16_mode_runs_and_reports_drift(hp):
     ref = _oracle(hp, weights, noise, mel)
     out, _ = _run(hp, weights, noise, mel, precision='bf16')
     err = np.abs(out.cpu().numpy() - ref).max()
-    print('bf16 default hparams max|delta| =', err)
-    assert np.isfinite(err) and err < 0.2
+    rms = float(np.sqrt(np.mean((out.cpu().numpy() - ref) ** 2)))
+    print('bf16 default hparams max|delta| =', err, 'rms =', rms)
+    # bf16 operands AND a bf16 residual stream (one bf16 plane in HBM): a float64 emulation of the storage rounding
+    # alone gives max|delta| 3.2e-2 on this case (8000 samples, |wav| <= 0.7); the survey's operand-only probe 2e-2
+    assert np.isfinite(err) and err <= 6e-2 and rms <= 1e-2
+    out0, _ = _run(hp, weights, noise, mel, precision='bf16', debug=LEGACY)      # fp32 residual stream, bf16 operands only
+    err0 = np.abs(out0.cpu().numpy() - ref).max()
+    print('bf16 (round-1 kernels: fp32 rows in HBM) max|delta| =', err0)
+    assert err0 <= 2e-2
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
@@ -192,16 +243,20 @@ def test_other_conditioning_widths(hp, n_mels, cc, precision):
 
 @pytest.mark.parametrize('channels', [64, 128])
 def test_use_skip_connection(hp, channels):
-    """model.use_skip_connection=True (reference modules.py:147: the post-net sees the SUM of every
-    layer's skip output); fp32 path, which 'auto' selects for it."""
+    """model.use_skip_connection=True (reference modules.py:147: the post-net sees the SUM of every layer's skip
+    output). 64 channels: gated layers on tcgen05 (every layer also emits z), skip sum and post-net on the exact fp32
+    kernels; 128 channels: fp32 path."""
     small_case(hp, channels=channels, dilations=((1, 2, 4, 512), (1, 8)), t=800, precision='auto')
     hp.model.use_skip_connection = True
     weights = pkg('weights').init_weights(hp, seed=13, bias_std=0.1)
     noise, mel = O.synthetic_inputs(2, 800, 80, 80)
     d = pkg('weights').model_dims(hp)
     ref = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], True, True, dtype=np.float64)
-    out, model = _run(hp, weights, noise, mel)
-    assert model.precision == 'fp32'
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)
+        out, model = _run(hp, weights, noise, mel)
+    assert model.precision == ('f16x3' if channels == 64 else 'fp32')
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
     hp.model.use_skip_connection = False
     ref_noskip = O.iaf_vocoder_forward(noise, mel, weights, d['dilations'], d['hop'], True, False, dtype=np.float64)
@@ -237,11 +292,12 @@ def test_properties_at_c3_size(hp, precision):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
-@pytest.mark.parametrize('variant', [1])
-def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision):
-    """The gated-layer kernel variant PWV_TC_VARIANT=1 (packed fp32x2 epilogue arithmetic) performs the same
-    IEEE operations per element as variant 0, so its output must be BIT-identical to it -- on the default graph, on ragged / d >= T edge shapes and on a
-    one-tile-per-CTA-slot case -- and (f16x3) within TOL of the oracle."""
+@pytest.mark.parametrize('path,variant', [(1, 1), (0, 1), (0, 2)])
+def test_layer_kernel_variants_bit_identical(hp, path, variant, precision):
+    """Kernel variants that perform the same IEEE operations per element as variant 0 must be BIT-identical to it -- on
+    the default graph, on ragged / d >= T edge shapes and on a one-tile-per-CTA-slot case -- and (f16x3) within TOL of
+    the oracle. variant 1: packed fp32x2 epilogue arithmetic (both paths); variant 2 (path 0): the round-1 kernels with
+    the setmaxnreg register re-partition."""
     W = pkg('weights')
     cases = [('default', None, 2, 4000), ('edge', ((1, 512, 2), (256, 1)), 5, 1040), ('edge', ((1, 512, 2), (256, 1)), 1, 80),
              ('default', None, 8, 16000)]
@@ -253,10 +309,8 @@ def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision
             hp.engine.precision = precision
         weights = W.init_weights(hp, seed=2, bias_std=0.1)
         noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=21, noise_seed=22)
-        monkeypatch.setenv('PWV_TC_VARIANT', '0')
-        base, _ = _run(hp, weights, noise, mel, precision=precision)
-        monkeypatch.setenv('PWV_TC_VARIANT', str(variant))
-        got, model = _run(hp, weights, noise, mel, precision=precision)
+        base, _ = _run(hp, weights, noise, mel, precision=precision, debug={'path': path, 'variant': 0})
+        got, model = _run(hp, weights, noise, mel, precision=precision, debug={'path': path, 'variant': variant})
         again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
         assert torch.equal(got, again), (kind, n, t, 'not deterministic')
         assert torch.equal(got, base), (kind, n, t, float((got - base).abs().max()))
@@ -269,17 +323,14 @@ def test_layer_kernel_variants_bit_identical(hp, monkeypatch, variant, precision
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
 @pytest.mark.parametrize('quiet,rotate,seg', [(0, 0, 100), (0, 1, 100), (0, 1, 1), (0, 0, 3), (0, 0, 0)])
-def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision, quiet, rotate, seg):
-    """k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
-    the same tile pipeline as the one-launch-per-layer path (PWV_TC_FLOW=0): outputs must be BIT-identical,
+def test_flow_kernel_bit_identical_to_layer_kernels(hp, precision, quiet, rotate, seg):
+    """Round-1 kernels (debug path 0). k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
+    the same tile pipeline as the one-launch-per-layer path (switch flow=0): outputs must be BIT-identical,
     including one-tile CTAs (idle second slot), single-layer flows (no GEMM2 at all), d >= T and ragged tiles.
-    Covered with and without the per-layer rotation of the tile-to-CTA assignment (PWV_TC_ROTATE) and for every
-    launch segmentation (PWV_TC_SEG layers per launch: the whole flow, one layer, three layers -- a ragged last
-    segment --, 0 = launch form chosen by job size, the default). The experimental 512-thread form (PWV_TC_QUIET=1)
-    is not part of the product path and is not exercised here (profiles/r1_experiments_after_flow_kernel.txt)."""
-    monkeypatch.setenv('PWV_TC_QUIET', str(quiet))
-    monkeypatch.setenv('PWV_TC_ROTATE', str(rotate))
-    monkeypatch.setenv('PWV_TC_SEG', str(seg))
+    Covered with and without the per-layer rotation of the tile-to-CTA assignment (rotate) and for every
+    launch segmentation (seg layers per launch: the whole flow, one layer, three layers -- a ragged last
+    segment --, 0 = launch form chosen by job size)."""
+    switches = {'path': 0, 'rotate': rotate, 'seg': seg}
     W = pkg('weights')
     cases = [(None, 2, 4000), (((1, 512, 2), (256, 1)), 5, 1040), (((1, 512, 2), (256, 1)), 1, 80), (((1,), (2, 4), (128,)), 3, 2000),
              (((1, 2, 4, 8, 16, 32, 64, 128, 256, 512) * 3,), 4, 8000), (None, 8, 16000)]
@@ -291,10 +342,8 @@ def test_flow_kernel_bit_identical_to_layer_kernels(hp, monkeypatch, precision, 
             small_case(hp, dilations=dil, n=n, t=t, precision=precision)
         weights = W.init_weights(hp, seed=4, bias_std=0.1)
         noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=31, noise_seed=32)
-        monkeypatch.setenv('PWV_TC_FLOW', '0')
-        base, _ = _run(hp, weights, noise, mel, precision=precision)
-        monkeypatch.setenv('PWV_TC_FLOW', '1')
-        got, model = _run(hp, weights, noise, mel, precision=precision)
+        base, _ = _run(hp, weights, noise, mel, precision=precision, debug=dict(switches, flow=0))
+        got, model = _run(hp, weights, noise, mel, precision=precision, debug=dict(switches, flow=1))
         for _ in range(3):      # the handshake is timing dependent: repeat
             again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
             assert torch.equal(got, again), (dil, n, t, 'not deterministic')
