@@ -149,6 +149,23 @@ int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double
  * "seg", "rotate", "stagger", "variant", "trace_flow" -- see csrc/pwv_api.cu. Unknown keys fail with PWV_EINVAL. */
 int pwv_debug_set(pwv_model* m, const char* key, int value);
 
+/* ---- mel front end: the step immediately upstream of the path.
+ * Replaces reference audio.py:327-356 `wav2melspec_db` (librosa.stft -> |.| -> librosa.filters.mel -> amplitude_to_db
+ * -> normalize_db, called from data_load.py:37-56): centred STFT (periodic hann of win_length centred in n_fft,
+ * reflect padding), magnitude, mel basis, 20 log10(max(., 1e-5)), floor at (utterance max - 80 dB), and, when
+ * `normalise`, clip((db - min_db) / (max_db - min_db), 0, 1) * 2 - 1. The caller supplies the mel basis
+ * [n_mels][1 + n_fft/2] (HOST pointer; librosa.filters.mel(sr, n_fft, n_mels): melspec.mel_basis). */
+typedef struct pwv_mel_config {
+  int32_t n_fft, win_length, hop_length, n_mels;   /* signal.n_fft / win_length / hop_length / n_mels; n_fft a power of two */
+  float min_db, max_db;                            /* signal.min_db / max_db                                              */
+  int32_t normalise;                               /* 0: raw dB (after the top_db floor)                                    */
+} pwv_mel_config;
+typedef struct pwv_melspec pwv_melspec;            /* opaque */
+int pwv_melspec_create(const pwv_mel_config* cfg, const float* mel_basis, pwv_melspec** out);
+int pwv_melspec_destroy(pwv_melspec* h);
+/* wav [N][T] -> mel [N][1 + T/hop][n_mels], DEVICE pointers, asynchronous on `stream`; T > n_fft/2. */
+int pwv_melspec_forward(pwv_melspec* h, const float* wav, float* mel, int N, int T, pwv_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

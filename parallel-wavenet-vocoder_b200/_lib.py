@@ -21,6 +21,7 @@ EXPORTS = (
     'pwv_model_num_variables', 'pwv_model_variable', 'pwv_model_load_weight', 'pwv_model_finalize',
     'pwv_workspace_bytes', 'pwv_forward', 'pwv_forward_host', 'pwv_last_launch_count',
     'pwv_set_profiling', 'pwv_profile_read', 'pwv_debug_set_trace', 'pwv_debug_set',
+    'pwv_melspec_create', 'pwv_melspec_destroy', 'pwv_melspec_forward',
 )
 
 
@@ -37,6 +38,11 @@ class PwvHparams(ctypes.Structure):
         ('cond_upsample', ctypes.c_int32), ('n_upsample', ctypes.c_int32),
         ('upsample_strides', ctypes.c_int32 * PWV_MAX_UPSAMPLE),
     ]
+
+
+class PwvMelConfig(ctypes.Structure):
+    _fields_ = [('n_fft', ctypes.c_int32), ('win_length', ctypes.c_int32), ('hop_length', ctypes.c_int32), ('n_mels', ctypes.c_int32),
+                ('min_db', ctypes.c_float), ('max_db', ctypes.c_float), ('normalise', ctypes.c_int32)]
 
 
 class PwvTaps(ctypes.Structure):
@@ -85,6 +91,9 @@ def load():
     lib.pwv_set_profiling.argtypes = [c.c_void_p, c.c_int]
     lib.pwv_debug_set_trace.argtypes = [c.c_void_p, c.c_void_p, c.c_int]
     lib.pwv_debug_set.argtypes = [c.c_void_p, c.c_char_p, c.c_int]
+    lib.pwv_melspec_create.argtypes = [c.POINTER(PwvMelConfig), c.c_void_p, c.POINTER(c.c_void_p)]
+    lib.pwv_melspec_destroy.argtypes = [c.c_void_p]
+    lib.pwv_melspec_forward.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     lib.pwv_profile_read.argtypes = [c.c_void_p, c.POINTER(c.c_double), c.POINTER(c.c_int), c.POINTER(c.c_double)]
     for name in EXPORTS:
         if name not in ('pwv_last_error',):

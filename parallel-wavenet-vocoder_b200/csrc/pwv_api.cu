@@ -18,6 +18,7 @@
 #include "pwv_simt.cuh"
 #include "pwv_tc.cuh"
 #include "pwv_tc2.cuh"
+#include "pwv_mel.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -1234,6 +1235,105 @@ int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double
   }
   if (layer_ms) *layer_ms = sum;
   if (layer_launches) *layer_launches = m->prof_launches > 0 ? m->prof_launches : n;
+  return PWV_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// mel front end (reference data_load.py:37-56 / audio.py:327-356), see pwv_mel.cuh
+// ------------------------------------------------------------------------------------------------
+struct pwv_melspec {
+  pwv_mel_config cfg;
+  int bins = 0, win_lo = 0, win_hi = 0;
+  float* d_window = nullptr;
+  float2* d_twiddle = nullptr;
+  float* d_basis = nullptr;
+  int* d_band = nullptr;       // [2][n_mels]
+  int* d_max = nullptr;
+  int max_cap = 0;
+};
+
+extern "C" {
+
+int pwv_melspec_create(const pwv_mel_config* cfg, const float* mel_basis, pwv_melspec** out) {
+  if (!cfg || !mel_basis || !out) return fail(PWV_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->n_fft < 2 || (cfg->n_fft & (cfg->n_fft - 1)) != 0) return fail(PWV_EINVAL, "n_fft=%d must be a power of two", cfg->n_fft);
+  if (cfg->win_length < 1 || cfg->win_length > cfg->n_fft) return fail(PWV_EINVAL, "win_length=%d must be in [1, n_fft=%d]", cfg->win_length, cfg->n_fft);
+  if (cfg->hop_length < 1 || cfg->n_mels < 1) return fail(PWV_EINVAL, "bad hop_length/n_mels (%d/%d)", cfg->hop_length, cfg->n_mels);
+  if (cfg->normalise && !(cfg->max_db > cfg->min_db)) return fail(PWV_EINVAL, "normalisation needs max_db > min_db");
+  pwv_melspec* h = new (std::nothrow) pwv_melspec();
+  if (!h) return fail(PWV_ENOMEM, "out of host memory");
+  h->cfg = *cfg;
+  const int n_fft = cfg->n_fft, win = cfg->win_length, n_mels = cfg->n_mels;
+  h->bins = 1 + n_fft / 2;
+  h->win_lo = (n_fft - win) / 2;            // the window is centred in the frame (torch.stft / librosa pad_center)
+  h->win_hi = h->win_lo + win;
+  std::vector<float> window(n_fft, 0.f);
+  std::vector<float2> tw(n_fft);
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < win; ++i) window[h->win_lo + i] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * i / win));   // periodic hann
+  for (int i = 0; i < n_fft; ++i) tw[i] = make_float2((float)std::cos(2.0 * PI * i / n_fft), (float)(-std::sin(2.0 * PI * i / n_fft)));
+  std::vector<int> band(2 * n_mels);
+  for (int m = 0; m < n_mels; ++m) {
+    int lo = h->bins, hi = 0;
+    for (int k = 0; k < h->bins; ++k)
+      if (mel_basis[(size_t)m * h->bins + k] != 0.f) { lo = k < lo ? k : lo; hi = k + 1; }
+    if (hi <= lo) lo = hi = 0;
+    band[m] = lo;
+    band[n_mels + m] = hi;
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  const bool ok = up((void**)&h->d_window, window.data(), sizeof(float) * n_fft) && up((void**)&h->d_twiddle, tw.data(), sizeof(float2) * n_fft) &&
+                  up((void**)&h->d_basis, mel_basis, sizeof(float) * (size_t)n_mels * h->bins) && up((void**)&h->d_band, band.data(), sizeof(int) * band.size());
+  if (!ok) {
+    cudaError_t e = cudaGetLastError();
+    pwv_melspec_destroy(h);
+    return fail(PWV_ECUDA, "mel front end: device upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return PWV_OK;
+}
+
+int pwv_melspec_destroy(pwv_melspec* h) {
+  if (!h) return PWV_OK;
+  cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_basis); cudaFree(h->d_band); cudaFree(h->d_max);
+  delete h;
+  return PWV_OK;
+}
+
+int pwv_melspec_forward(pwv_melspec* h, const float* wav, float* mel, int N, int T, pwv_stream stream) {
+  if (!h || !wav || !mel) return fail(PWV_EINVAL, "null argument");
+  if (N < 1 || T < 1 || N > 65535) return fail(PWV_EINVAL, "N=%d, T=%d out of range", N, T);
+  if (T <= h->cfg.n_fft / 2) return fail(PWV_EINVAL, "T=%d: reflect padding needs more than n_fft/2 = %d samples", T, h->cfg.n_fft / 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > h->max_cap) {                 // per-utterance maxima: grown on demand (the only allocation of this entry point)
+    if (h->d_max) cudaFree(h->d_max);
+    h->d_max = nullptr;
+    h->max_cap = 0;
+    PWV_CUDA(cudaMalloc(&h->d_max, sizeof(int) * (size_t)N));
+    h->max_cap = N;
+  }
+  pwv::MelParams p;
+  p.wav = wav; p.out = mel; p.window = h->d_window; p.twiddle = h->d_twiddle; p.basis = h->d_basis;
+  p.band_lo = h->d_band; p.band_hi = h->d_band + h->cfg.n_mels; p.utt_max = h->d_max;
+  p.N = N; p.T = T; p.t_mel = 1 + T / h->cfg.hop_length; p.n_fft = h->cfg.n_fft; p.hop = h->cfg.hop_length; p.n_mels = h->cfg.n_mels;
+  p.bins = h->bins; p.win_lo = h->win_lo; p.win_hi = h->win_hi;
+  p.amin = 1e-5f; p.top_db = 80.f;      // librosa.amplitude_to_db defaults, what reference audio.py:254-262 relies on
+  p.min_db = h->cfg.min_db; p.max_db = h->cfg.max_db; p.normalise = h->cfg.normalise;
+  const int span = (pwv::MEL_FB - 1) * p.hop + p.n_fft;
+  const size_t smem = sizeof(float) * ((span + 3) & ~3) + sizeof(float2) * p.n_fft + sizeof(float) * pwv::MEL_FB * (p.bins + 1);
+  if (smem > 48 * 1024) return fail(PWV_EINVAL, "mel front end: n_fft=%d / hop=%d need %zu bytes of shared memory (> 48 KB)", p.n_fft, p.hop, smem);
+  pwv::k_mel_init<<<(N + 255) / 256, 256, 0, st>>>(h->d_max, N);
+  dim3 grid((p.t_mel + pwv::MEL_FB - 1) / pwv::MEL_FB, N);
+  pwv::k_mel_power<<<grid, pwv::MEL_THREADS, smem, st>>>(p);
+  const size_t total = (size_t)N * p.t_mel * p.n_mels;
+  pwv::k_mel_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  PWV_CUDA(cudaGetLastError());
   return PWV_OK;
 }
 

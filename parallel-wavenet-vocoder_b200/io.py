@@ -54,7 +54,8 @@ class GenerationData:
             raise FileNotFoundError(f'no wav files match data_path {hp.data_path!r}')
         wavs, mels = [], []
         for i in range(n):                       # the reference batches consecutive (shuffled) files; here: in order
-            wav, mel = melspec.wav_and_melspec(self.wav_files[i % len(self.wav_files)], hp.signal, t)
+            wav, mel = melspec.wav_and_melspec(self.wav_files[i % len(self.wav_files)], hp.signal, t,
+                                               device='cuda' if torch.cuda.is_available() else 'cpu')
             wavs.append(wav)
             mels.append(mel)
         return np.stack(wavs), np.stack(mels), None

@@ -125,12 +125,59 @@ def wav2melspec_db(wav, sr, n_fft, win_length, hop_length, n_mels, max_db=None, 
     return out[0] if squeeze else out
 
 
+class MelFrontEnd:
+    """wav2melspec_db on the GPU through the C-ABI (`pwv_melspec_*`, csrc/pwv_mel.cuh): device waveform in, device
+    mel out, no host round trip. The CPU function above is its restated checker (tests/test_gpu_melspec.py)."""
+
+    def __init__(self, sr, n_fft, win_length, hop_length, n_mels, max_db=None, min_db=None):
+        import ctypes
+        from . import _lib
+        self._lib_mod, self.lib = _lib, _lib.load()
+        self.hop, self.n_mels = int(hop_length), int(n_mels)
+        cfg = _lib.PwvMelConfig()
+        cfg.n_fft, cfg.win_length, cfg.hop_length, cfg.n_mels = int(n_fft), int(win_length), int(hop_length), int(n_mels)
+        cfg.normalise = int(bool(max_db and min_db))
+        cfg.min_db, cfg.max_db = float(min_db or 0.0), float(max_db or 0.0)
+        basis = np.ascontiguousarray(mel_basis(sr, n_fft, n_mels), dtype=np.float32)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.pwv_melspec_create(ctypes.byref(cfg), basis.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._h)))
+
+    def __call__(self, wav):
+        """(N, T) float32 CUDA tensor -> (N, 1 + T // hop, n_mels) float32 CUDA tensor (asynchronous on the current stream)."""
+        import ctypes
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2
+        wav = wav.contiguous()
+        n, t = wav.shape
+        out = torch.empty((n, 1 + t // self.hop, self.n_mels), dtype=torch.float32, device=wav.device)
+        stream = torch.cuda.current_stream(wav.device).cuda_stream
+        with torch.cuda.device(wav.device):
+            self._lib_mod.check(self.lib.pwv_melspec_forward(self._h, wav.data_ptr(), out.data_ptr(), n, t, ctypes.c_void_p(stream)))
+        return out
+
+    def close(self):
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            self.lib.pwv_melspec_destroy(h)
+            h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def wav_and_melspec(path, hp_signal, length, device='cpu'):
     """reference data_load.py:37-56 for generation: -> (wav (length, 1) f32, melspec (1+length//hop, n_mels) f32)."""
     wav = read_wav(path, sr=int(hp_signal.sr))
     wav = trim_wav(wav)
     wav = fix_length(wav[:length], length)
-    mel = wav2melspec_db(wav, sr=int(hp_signal.sr), n_fft=int(hp_signal.n_fft), win_length=int(hp_signal.win_length),
-                         hop_length=int(hp_signal.hop_length), n_mels=int(hp_signal.n_mels),
-                         max_db=hp_signal.max_db, min_db=hp_signal.min_db, device=device)
+    if str(device).startswith('cuda'):
+        front = MelFrontEnd(int(hp_signal.sr), int(hp_signal.n_fft), int(hp_signal.win_length), int(hp_signal.hop_length),
+                            int(hp_signal.n_mels), max_db=hp_signal.max_db, min_db=hp_signal.min_db)
+        mel = front(torch.from_numpy(wav)[None].to(device))[0]
+    else:
+        mel = wav2melspec_db(wav, sr=int(hp_signal.sr), n_fft=int(hp_signal.n_fft), win_length=int(hp_signal.win_length),
+                             hop_length=int(hp_signal.hop_length), n_mels=int(hp_signal.n_mels),
+                             max_db=hp_signal.max_db, min_db=hp_signal.min_db, device=device)
     return wav[:, None].astype(np.float32), mel.cpu().numpy().astype(np.float32)
