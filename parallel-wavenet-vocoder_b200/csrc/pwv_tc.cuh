@@ -454,13 +454,16 @@ __device__ __forceinline__ void tc_prep(uint8_t* box_row, int r, uint32_t taddr_
   }
 }
 // Register re-partition between the warp roles (setmaxnreg works per warpgroup = 4 consecutive warps): the kernels
-// launch with 640 threads x 96 registers; the helper warpgroup (warps 16-19: MMA issuers, TMA producers) hands
-// registers back, the four worker warpgroups take them (512 x 120 + 128 x 32 = 65,536 = the whole register file).
+// launch with 640 threads x 96 registers = 61,440, which is the CTA's register pool -- setmaxnreg only moves registers
+// INSIDE that pool (SASS: USETMAXREG.*.CTAPOOL); the SM's unallocated remainder is not available (round-2 measurement:
+// a split that summed to 65,536 spun forever in TRY_ALLOC). The helper warpgroup (warps 16-19: MMA issuers, TMA
+// producers) hands registers back, the four worker warpgroups take them: 512 x 112 + 128 x 32 = 61,440.
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-constexpr int TC_WORKER_REGS = 120, TC_HELPER_REGS = 32;
+constexpr int TC_WORKER_REGS = 112, TC_HELPER_REGS = 32;
+static_assert(TC_WORKER_REGS * 512 + TC_HELPER_REGS * 128 <= 96 * 640, "setmaxnreg redistributes the CTA's launch allocation only");
 constexpr int TC_WORKER_WARPS = 16;                       // 2 tile slots x 2 channel halves x 4 lane quarters
 constexpr int TC_MMA_WARP = 16;                           // 16, 17: MMA issuer of tile slot 0, 1
 constexpr int TC_TMA_WARP = 18;                           // 18, 19: TMA producer of tile slot 0, 1

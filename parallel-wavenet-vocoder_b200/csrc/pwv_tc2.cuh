@@ -26,7 +26,8 @@
 //     runs) -> residual(j) + hi/lo split -> staged in the x[t] boxes -> TMA store by the producer warp -> x[t] boxes
 //     refilled for j+2. The residual arithmetic and the store of tile j overlap GEMM1 of tile j+1.
 //   * Registers: 640 threads launch with 96 registers; the helper warpgroup (MMA issuers, producers) drops to
-//     TH_HELPER_REGS and the four worker warpgroups rise to TH_WORKER_REGS (setmaxnreg; ptxas allocates per branch).
+//     TH_HELPER_REGS and the four worker warpgroups rise to TH_WORKER_REGS (setmaxnreg moves registers inside the CTA's
+//     launch allocation of 640 x 96; ptxas allocates each role's branch with its own budget).
 // Weights, TMEM slot layout (D1 128 | Ahi 64 | Alo 64), arithmetic (f16x3 / bf16, gate formulas, epilogue scales),
 // tile-to-CTA assignment, programmatic dependent launch and the per-tile flag handshake between consecutive layers
 // are those of k_layer_tc (pwv_tc.cuh).
@@ -41,7 +42,9 @@ constexpr int TH_SMEM_STAGE0 = ((TC_IMAGE_BYTES + 1023) / 1024) * 1024;
 constexpr int TH_SMEM_CB0 = TH_SMEM_STAGE0 + 2 * TH_STAGE_BYTES;      // [slot][tile parity] conditioning rows
 constexpr int TH_SMEM_BARS = TH_SMEM_CB0 + 4 * TC_CB_BYTES;
 constexpr int TH_SMEM_BYTES = TH_SMEM_BARS + 256;
-constexpr int TH_WORKER_REGS = 120, TH_HELPER_REGS = 32;   // 512 x 120 + 128 x 32 = 65,536: the whole register file
+constexpr int TH_WORKER_REGS = 112, TH_HELPER_REGS = 32;   // 512 x 112 + 128 x 32 = 61,440 = 640 x 96, the CTA's launch allocation
+
+static_assert(TH_WORKER_REGS * 512 + TH_HELPER_REGS * 128 <= 96 * 640, "setmaxnreg redistributes the CTA's launch allocation only (pwv_tc.cuh)");
 
 struct ThLayerParams {
   const uint8_t* image[2];  // per body: the layer's weight image (TC_IMAGE_BYTES, as for k_layer_tc)
