@@ -67,7 +67,7 @@ struct BodyOff {
 };
 
 #ifndef PWV_TC_VARIANT_DEFAULT
-#define PWV_TC_VARIANT_DEFAULT 0
+#define PWV_TC_VARIANT_DEFAULT 1
 #endif
 
 struct pwv_model {
@@ -113,6 +113,8 @@ struct pwv_model {
   int tc_seg = 0;                // "seg" (path 0): k_flow_tc gated layers per launch (0 = by job size)
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // "variant": 0 scalar epilogue arithmetic, 1 packed fp32x2, 2 (path 0) setmaxnreg register re-partition
   bool trace_flow = false;       // "trace_flow" (path 0): the phase trace follows k_flow_tc instead of forcing per-layer launches
+  bool split1 = true;            // "split1" (path 1): GEMM1 starts on the x[t-d] half of K before the x[t] boxes are copied
+  bool split2 = true;            // "split2" (path 1): GEMM2 starts on the first half of the z chunks
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
                                  // 2: one pair around each flow's chain of gated-layer launches (as in production)
@@ -572,7 +574,7 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   w->flags_bytes = 0;
   if (m->hp.precision != PWV_PREC_FP32) {
     const size_t tiles_body = (size_t)N * ((T + pwv::TC_TM - 1) / pwv::TC_TM);
-    w->flags_bytes = sizeof(int) * (size_t)m->total_layers * 2 * tiles_body;
+    w->flags_bytes = sizeof(int) * ((size_t)m->total_layers * 2 * tiles_body + m->total_layers);   // + a completion counter per layer
     w->flags = (int*)take(w->flags_bytes);
   }
   w->bytes = off;
@@ -910,6 +912,14 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
     p.flags_out = (layer_flags && j + 1 < L) ? fl : nullptr;
     p.flags_in = (layer_flags && j > 0) ? fl - 2 * (size_t)tiles_body : nullptr;
     p.prev_dilation = j > 0 ? hp.dilations[flow][j - 1] : 0;
+    {
+      int* done = w.flags + (size_t)m->total_layers * 2 * tiles_body + layer_base / 2 + j;
+      p.done_out = p.flags_out ? done : nullptr;
+      p.done_in = p.flags_in ? done - 1 : nullptr;
+      p.done_target = 2 * grid;          // both producers of every CTA of the previous layer's grid (same grid for the whole flow)
+    }
+    p.split1 = m->split1 ? 1 : 0;
+    p.split2 = m->split2 ? 1 : 0;
     p.z_out = (hp.use_skip_connection && !last) ? w.zbuf : nullptr;
     p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
     if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
@@ -924,7 +934,7 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = (m->profiling == 1 || !m->use_pdl) ? 0 : 1;
-      const bool pk = m->tc_variant == 1;
+      const bool pk = m->tc_variant != 0;
       const CUtensorMap& in = maps_h[cur];
       const CUtensorMap& out = last ? maps_f[cur ^ 1] : maps_h[cur ^ 1];
       cudaError_t e;
@@ -1208,6 +1218,8 @@ int pwv_debug_set(pwv_model* m, const char* key, int value) {
   else if (k == "seg") m->tc_seg = value;
   else if (k == "variant") { if (value < 0 || value > 2) return fail(PWV_EINVAL, "variant must be 0, 1 or 2"); m->tc_variant = value; }
   else if (k == "trace_flow") m->trace_flow = value != 0;
+  else if (k == "split1") m->split1 = value != 0;
+  else if (k == "split2") m->split2 = value != 0;
   else return fail(PWV_EINVAL, "unknown debug switch '%s'", key);
   return PWV_OK;
 }

@@ -57,12 +57,21 @@ struct ThLayerParams {
   const int* flags_in;      // tile handshake with the previous gated layer (see TcLayerParams)
   int* flags_out;
   int prev_dilation;
+  // Whole-layer completion counters (one int per layer, zeroed with the flags): a CTA adds 1 when all its tiles are
+  // stored. Once a producer has seen the previous layer's counter at `done_target` every tile it could wait for is
+  // published, and the per-tile probes (5 gpu-scope loads + an acquire fence + a proxy fence: ~3k cycles per tile on
+  // the producer's serial path, profiles/r2_trace_layer_h_v1.txt) are skipped for the rest of the launch.
+  const int* done_in;
+  int* done_out;
+  int done_target;
+  int split1;               // 1: GEMM1 starts on the x[t-d] half of K as soon as those columns are copied (the x[t] boxes land later)
+  int split2;               // 1: GEMM2 starts on the first 16-channel chunk of each half of z while the gate computes the second
   long long* trace;
 };
 
 struct ThBarriers {
   uint64_t w_ready;
-  uint64_t x_full[2], y_full[2], a_ready[2], d1_ready[2], z_ready[2], d2_ready[2], out_ready[2];
+  uint64_t x_full[2], y_full[2], ax_ready[2], ay_ready[2], d1_ready[2], za_ready[2], zb_ready[2], d2_ready[2], out_ready[2];
   uint32_t tmem_base;
   int mma_lock;
 };
@@ -105,9 +114,11 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       for (int s = 0; s < 2; ++s) {
         mbar_init(&bars->x_full[s], 1);
         mbar_init(&bars->y_full[s], 1);
-        mbar_init(&bars->a_ready[s], 256);
+        mbar_init(&bars->ax_ready[s], 256);
+        mbar_init(&bars->ay_ready[s], 256);
         mbar_init(&bars->d1_ready[s], 1);
-        mbar_init(&bars->z_ready[s], 256);
+        mbar_init(&bars->za_ready[s], 256);
+        mbar_init(&bars->zb_ready[s], 256);
         mbar_init(&bars->d2_ready[s], 1);
         mbar_init(&bars->out_ready[s], 256);
       }
@@ -149,37 +160,69 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       const uint32_t tD = tmem + s * 256;
       const uint32_t tAhi = tD + 128, tAlo = tD + 192;
       const int tiles_s = (n_local + 1 - s) / 2;
-      for (int j = 0; j < tiles_s; ++j) {
-        mbar_wait(&bars->a_ready[s], j & 1);
-        tc_lock<SPLIT>(&bars->mma_lock);
-        tc_fence_after_sync();
-        TC_TRACE(2, j, s * 8 + 0);
-        uint32_t acc = 0;
+      // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi over K steps [k0, k1) (a step = 16 channels = 8 TMEM columns of A and two
+      // 16-byte K-chunks of B); D2 likewise over the listed steps of z.
+      auto gemm1_part = [&](int k0, int k1, uint32_t acc) {
         if (SPLIT) {
 #pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
+          for (int ks = k0; ks < k1; ++ks, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
 #pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) mma_f16_ts(tD, tAhi + ks * 8, dW1lo + (uint64_t)(ks * 256), ID1, 1);
+          for (int ks = k0; ks < k1; ++ks) mma_f16_ts(tD, tAhi + ks * 8, dW1lo + (uint64_t)(ks * 256), ID1, 1);
         }
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ++ks, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
+        for (int ks = k0; ks < k1; ++ks, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
+      };
+      auto gemm2_part = [&](int k0, int kstep, uint32_t acc) {      // steps k0, k0 + kstep, ... < 4
+        if (SPLIT) {
+#pragma unroll 1
+          for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
+#pragma unroll 1
+          for (int ks = k0; ks < 4; ks += kstep) mma_f16_ts(tD, tAhi + ks * 8, dW2lo + (uint64_t)(ks * 128), ID2, 1);
+        }
+#pragma unroll 1
+        for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
+      };
+      for (int j = 0; j < tiles_s; ++j) {
+        const uint32_t par = j & 1;
+        mbar_wait(&bars->ax_ready[s], par);
+        if (p.split1) {                    // the x[t-d] half of K (columns copied first) ...
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TC_TRACE(2, j, s * 8 + 0);
+          gemm1_part(0, 4, 0);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+        }
+        mbar_wait(&bars->ay_ready[s], par);
+        tc_lock<SPLIT>(&bars->mma_lock);
+        tc_fence_after_sync();
+        if (p.split1) {                    // ... then the x[t] half
+          gemm1_part(4, 8, 1);
+        } else {
+          TC_TRACE(2, j, s * 8 + 0);
+          gemm1_part(0, 8, 0);
+        }
         mma_commit(&bars->d1_ready[s]);
         tc_unlock<SPLIT>(&bars->mma_lock);
         TC_TRACE(2, j, s * 8 + 1);
         if (LAST) continue;
-        mbar_wait(&bars->z_ready[s], j & 1);
+        // z columns: step 0 / 1 = first / second 16-channel chunk of the workers' half 0, steps 2 / 3 of half 1
+        mbar_wait(&bars->za_ready[s], par);
+        if (p.split2) {
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TC_TRACE(2, j, s * 8 + 2);
+          gemm2_part(0, 2, 0);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+        }
+        mbar_wait(&bars->zb_ready[s], par);
         tc_lock<SPLIT>(&bars->mma_lock);
         tc_fence_after_sync();
-        TC_TRACE(2, j, s * 8 + 2);
-        acc = 0;
-        if (SPLIT) {
-#pragma unroll 1
-          for (int ks = 0; ks < 4; ++ks, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
-#pragma unroll 1
-          for (int ks = 0; ks < 4; ++ks) mma_f16_ts(tD, tAhi + ks * 8, dW2lo + (uint64_t)(ks * 128), ID2, 1);
+        if (p.split2) {
+          gemm2_part(1, 2, 1);
+        } else {
+          TC_TRACE(2, j, s * 8 + 2);
+          gemm2_part(0, 1, 0);
         }
-#pragma unroll 1
-        for (int ks = 0; ks < 4; ++ks, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
         mma_commit(&bars->d2_ready[s]);
         tc_unlock<SPLIT>(&bars->mma_lock);
         TC_TRACE(2, j, s * 8 + 3);
@@ -220,8 +263,15 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 #pragma unroll
         for (int q = 0; q < P; ++q) tma_load_3d(st + (2 + q) * TH_BOX_BYTES, &map_in, 0, t0, q * 2 * p.N + ub0 + n, &bars->y_full[s]);
       };
+      bool prev_done = p.flags_in == nullptr;           // no handshake: the whole previous kernel is waited for below
       auto wait_tiles = [&](int j) {                    // see k_layer_tc: the previous layer's tiles this tile reads / overwrites
-        if (!p.flags_in) return;
+        if (prev_done) return;
+        if (ld_relaxed_gpu(p.done_in) >= p.done_target) {      // the previous layer has stored every tile
+          fence_acq_rel_gpu();
+          fence_proxy_async_global();
+          prev_done = true;
+          return;
+        }
         const int tile = tile_of(j);
         const int n = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * TC_TM;
         const int k = t0 / TC_TM, last = p.tiles_per_utt - 1;
@@ -237,6 +287,12 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         fence_acq_rel_gpu();
         fence_proxy_async_global();
       };
+      auto publish = [&](int j) {                       // tile j's rows are in global memory: let the next layer read them
+        bulk_wait0();
+        fence_proxy_async_global();
+        fence_acq_rel_gpu();
+        st_relaxed_gpu(p.flags_out + (size_t)body * tiles_body + tile_of(j), 1);
+      };
       if (!p.flags_in) pdl_wait_prior_grid();
       if (s == 1 && n_local > 0) mbar_wait(&bars->y_full[0], 0);       // half-phase stagger of the two slots
       if (tiles_s > 0) {
@@ -245,16 +301,16 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         issue_y(0);
       }
       if (tiles_s > 1) {                                // both landing areas are free once tile 0 sits in TMEM
-        mbar_wait(&bars->a_ready[s], 0);
         wait_tiles(1);
+        mbar_wait(&bars->ay_ready[s], 0);
         issue_x(1);
         issue_y(1);
       }
+      if (tiles_s > 2) wait_tiles(2);                   // the probes run one tile ahead, in the producer's idle time
       for (int j = 0; j < tiles_s; ++j) {
         if (j + 1 < tiles_s) {
-          mbar_wait(&bars->a_ready[s], (j + 1) & 1);    // tile j+1 copied into TMEM: the X boxes are free
+          mbar_wait(&bars->ax_ready[s], (j + 1) & 1);   // tile j+1's x[t-d] columns are in TMEM: the X boxes are free
           if (j + 2 < tiles_s) {
-            wait_tiles(j + 2);
             issue_x(j + 2);
             TC_TRACE(3, j, s * 8 + 0);
           }
@@ -276,14 +332,15 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         if (j + 2 < tiles_s) issue_y(j + 2);
         else if (j + 1 < tiles_s) mbar_arrive(&bars->y_full[s]);   // phase tiles_s: the slot's last tile waits for it before staging
         TC_TRACE(3, j, s * 8 + 2);
-        if (p.flags_out) {
-          bulk_wait0();                                 // the tile's rows are written
-          fence_proxy_async_global();
-          fence_acq_rel_gpu();
-          st_relaxed_gpu(p.flags_out + (size_t)body * tiles_body + tile_of(j), 1);
-        }
+        if (p.flags_out) publish(j);
+        if (j + 3 < tiles_s) wait_tiles(j + 3);
       }
       bulk_wait0();
+      if (p.done_out) {                                 // this slot's share of the CTA is stored (2 arrivals per CTA)
+        fence_proxy_async_global();
+        fence_acq_rel_gpu();
+        atomicAdd(p.done_out, 1);
+      }
     }
     __syncwarp();
    }
@@ -310,6 +367,9 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         th_ld_row64(stage + q * TH_BOX_BYTES, r, half * 4, v);
         tmem_st16((q ? tAlo : tAhi) + half * 16, v);
       }
+      tmem_wait_st();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->ax_ready[slot]);       // (the x[t-d] half of K: GEMM1 may start on it)
       mbar_wait(&bars->y_full[slot], par);
 #pragma unroll
       for (int q = 0; q < P; ++q) {
@@ -318,7 +378,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
       tmem_wait_st();
       tc_fence_before_sync();
-      mbar_arrive(&bars->a_ready[slot]);
+      mbar_arrive(&bars->ay_ready[slot]);
     };
 
     if (n_s > 0) {
@@ -374,6 +434,9 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
             split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
             tmem_st8(tAhi + half * 16 + c * 8, hi);
             if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+            tmem_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(c == 0 ? &bars->za_ready[slot] : &bars->zb_ready[slot]);
             if (p.z_out && t < p.T) {    // use_skip_connection (non-default): every layer's z feeds the skip sum (k_skip_simt)
               float4* zo = reinterpret_cast<float4*>(p.z_out + (((size_t)body * p.N + n) * p.T + t) * TC_C + half * 32 + c * 16);
 #pragma unroll
@@ -383,9 +446,6 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         }
       }
       if constexpr (!LAST) {
-        tmem_wait_st();
-        tc_fence_before_sync();
-        mbar_arrive(&bars->z_ready[slot]);
         if (tracer) TC_TRACE(slot, j, 6);
         // ---- D2 and x[t] (hi, lo) of my 32 channels -> registers; after this the slot's TMEM belongs to the next tile
         mbar_wait(&bars->d2_ready[slot], par);
