@@ -18,6 +18,7 @@
 #include "pwv_simt.cuh"
 #include "pwv_tc.cuh"
 #include "pwv_tc2.cuh"
+#include "pwv_tc3.cuh"
 #include "pwv_mel.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +96,7 @@ struct pwv_model {
   int num_sms = 148;
 
   pwv::TcModel tc;               // tensor-core weight images (empty in fp32 mode)
+  pwv::TwModel tw;               // weight streams of the wide tensor-core kernels (C > 64)
 
   // host-buffer entry point staging
   float* h_dev = nullptr;
@@ -113,8 +115,8 @@ struct pwv_model {
   int tc_seg = 0;                // "seg" (path 0): k_flow_tc gated layers per launch (0 = by job size)
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // "variant": 0 scalar epilogue arithmetic, 1 packed fp32x2, 2 (path 0) setmaxnreg register re-partition
   bool trace_flow = false;       // "trace_flow" (path 0): the phase trace follows k_flow_tc instead of forcing per-layer launches
-  bool split1 = true;            // "split1" (path 1): GEMM1 starts on the x[t-d] half of K before the x[t] boxes are copied
-  bool split2 = true;            // "split2" (path 1): GEMM2 starts on the first half of the z chunks
+  bool split1 = false;           // "split1" (path 1): GEMM1 starts on the x[t-d] half of K before the x[t] boxes are copied
+  bool split2 = false;           // "split2" (path 1): GEMM2 starts on the first half of the z chunks
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
   int profiling = 0;             // 1: event pair around every gated-layer launch (serialised, no PDL);
                                  // 2: one pair around each flow's chain of gated-layer launches (as in production)
@@ -231,6 +233,10 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<false, pwv::TW_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<false, pwv::TW_EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<true, pwv::TW_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<true, pwv::TW_EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_post_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TCP_SMEM_BYTES));
     if (m->tc.d_cond) {
@@ -283,8 +289,8 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   }
   if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_F16X3 && hp->precision != PWV_PREC_BF16)
     return fail(PWV_EINVAL, "unknown precision %d", hp->precision);
-  if (hp->precision != PWV_PREC_FP32 && C != 64)
-    return fail(PWV_EINVAL, "tensor-core precisions are implemented for residual_channels=64 only (got %d)", C);
+  if (hp->precision != PWV_PREC_FP32 && C != 64 && hp->use_skip_connection)
+    return fail(PWV_EINVAL, "use_skip_connection=True at %d channels runs on the fp32 path only (precision fp32)", C);
   int total = 0, mx = 0;
   for (int i = 0; i < hp->n_iaf; ++i) {
     if (hp->n_layers[i] < 1 || hp->n_layers[i] > PWV_MAX_LAYERS) return fail(PWV_EINVAL, "flow %d: %d layers out of range [1,%d]", i, hp->n_layers[i], PWV_MAX_LAYERS);
@@ -312,6 +318,7 @@ int pwv_model_destroy(pwv_model* m) {
   if (m->h_dev) cudaFree(m->h_dev);
   for (auto e : m->ev) cudaEventDestroy(e);
   pwv::tc_model_free(m->tc);
+  pwv::tw_model_free(m->tw);
   delete m;
   return PWV_OK;
 }
@@ -492,6 +499,14 @@ int pwv_model_finalize(pwv_model* m) {
         q.w2 = arena.data() + bo.w2; q.b2 = arena.data() + bo.b2;
         posts.push_back(q);
       }
+    if (C != pwv::TC_C) {       // wide channel counts: streamed-K kernels (pwv_tc3.cuh); conditioning and post-net stay on the fp32 kernels
+      const char* werr = pwv::tw_model_build(m->tw, hp.precision, C, src);
+      if (werr) return fail(PWV_ECUDA, "wide tensor-core weight streams: %s", werr);
+      const int rcw = configure_kernels(m);
+      if (rcw) return rcw;
+      m->finalized = true;
+      return PWV_OK;
+    }
     const char* err = pwv::tc_model_build(m->tc, hp.precision, C, src, posts);
     if (err) return fail(PWV_ECUDA, "tensor-core weight images: %s", err);
     // conditioning projections on the tensor cores too (when Cc allows it)
@@ -569,6 +584,8 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   if (m->hp.use_skip_connection) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
     w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
+  } else if (m->hp.precision != PWV_PREC_FP32 && C != pwv::TC_C) {
+    w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);     // z planes between the gate and the dense pass (k_wide_h)
   }
   w->flags = nullptr;
   w->flags_bytes = 0;
@@ -842,7 +859,7 @@ static int launch_layers_tc(pwv_model* m, const Workspace& w, const CUtensorMap*
 
 // 3-D TMA map of an activation buffer in the plane layout [planes * 2N utterance-bodies][T][64] 16-bit (fp16 hi / lo
 // planes, or one bf16 plane): box = 64 channels x 128 rows x 1 (16 KB), 128B swizzle, zero OOB fill.
-static int encode_plane_map(CUtensorMap* map, void* base, int N, int T, int planes, bool bf16) {
+static int encode_plane_map(CUtensorMap* map, void* base, int N, int T, int planes, bool bf16, int C = 64) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -854,8 +871,8 @@ static int encode_plane_map(CUtensorMap* map, void* base, int N, int T, int plan
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(PWV_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     encode = (EncodeFn)fn;
   }
-  const cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)planes * 2 * N};
-  const cuuint64_t strides[2] = {64 * 2, (cuuint64_t)T * 64 * 2};
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)planes * 2 * N};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
   const cuuint32_t box[3] = {64, (cuuint32_t)pwv::TC_TM, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
@@ -1001,6 +1018,92 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
   return PWV_OK;
 }
 
+
+// gated layers of one flow at C > 64 channels on the tensor cores (k_wide_h, pwv_tc3.cuh): per layer a gate pass
+// (x planes -> z planes) and a dense pass (z planes + x planes -> next x planes); the flow's last layer has no dense
+// pass. The post-net runs on the fp32 kernel from z converted back to fp32 rows.
+template <int C>
+static int launch_layers_w(pwv_model* m, const Workspace& w, const CUtensorMap* maps_h, const CUtensorMap& map_z, int flow, int N, int T,
+                           cudaStream_t st, const pwv_taps* taps, int* cur_buf, int* launches) {
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], t_mel = cond_rows(m, T), c_hop = cond_hop(m);
+  const bool bf16 = hp.precision == PWV_PREC_BF16;
+  const int tiles_per_utt = (T + pwv::TC_TM - 1) / pwv::TC_TM;
+  const int NB = C / 64;
+  const long long items = 2LL * N * tiles_per_utt * NB;
+  const int grid = items < m->num_sms ? (int)items : m->num_sms;
+  size_t layer_base = 0;
+  for (int i = 0; i < flow; ++i) layer_base += 2 * (size_t)hp.n_layers[i];
+  const size_t plane_elems = (size_t)2 * N * T * C;
+  int cur = *cur_buf;
+  for (int j = 0; j < L; ++j) {
+    const bool last = j == L - 1;
+    pwv::TwParams p;
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = c_hop; p.dilation = hp.dilations[flow][j]; p.tiles_per_utt = tiles_per_utt;
+    p.NB = NB; p.C_out = C;
+    for (int b = 0; b < 2; ++b) {
+      const size_t li = layer_base + (size_t)b * L + j;
+      p.wimg[b] = m->tw.d_gate + li * m->tw.gate_bytes;
+      p.vec[b] = m->tw.d_vec + li * m->tw.vec_floats;
+      p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
+    }
+    p.KB = 2 * C / 64; p.KB_tap = C / 64;
+    if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
+    if (bf16) pwv::k_wide_h<true, pwv::TW_EPI_GATE><<<grid, pwv::TW_THREADS, pwv::TW_SMEM_BYTES, st>>>(maps_h[cur], maps_h[cur], map_z, p);
+    else pwv::k_wide_h<false, pwv::TW_EPI_GATE><<<grid, pwv::TW_THREADS, pwv::TW_SMEM_BYTES, st>>>(maps_h[cur], maps_h[cur], map_z, p);
+    ++*launches;
+    if (!last) {
+      for (int b = 0; b < 2; ++b) p.wimg[b] = m->tw.d_dense + (layer_base + (size_t)b * L + j) * m->tw.dense_bytes;
+      p.KB = C / 64; p.KB_tap = p.KB; p.dilation = 0;
+      if (bf16) pwv::k_wide_h<true, pwv::TW_EPI_DENSE><<<grid, pwv::TW_THREADS, pwv::TW_SMEM_BYTES, st>>>(map_z, maps_h[cur], maps_h[cur ^ 1], p);
+      else pwv::k_wide_h<false, pwv::TW_EPI_DENSE><<<grid, pwv::TW_THREADS, pwv::TW_SMEM_BYTES, st>>>(map_z, maps_h[cur], maps_h[cur ^ 1], p);
+      ++*launches;
+    } else {      // z planes -> fp32 rows in the other activation buffer: the post-net kernel's input
+      const size_t pairs = plane_elems / 2;
+      const unsigned blocks = (unsigned)((pairs + 255) / 256);
+      if (bf16) pwv::k_planes_to_f32_n<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(w.zbuf), w.act[cur ^ 1], pairs, plane_elems);
+      else pwv::k_planes_to_f32_n<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(w.zbuf), w.act[cur ^ 1], pairs, plane_elems);
+      ++*launches;
+    }
+    if (m->profiling == 1 || (m->profiling == 2 && last)) PWV_PROF_MARK(m, st);
+    if (m->profiling) ++m->prof_launches;
+    cur ^= 1;
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1)) {
+      const size_t rows = (size_t)N * T;
+      if (last) {
+        PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * rows * C, sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
+      } else {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(w.act[cur]) + (size_t)taps->layer_body * rows * C;
+        const size_t pairs = rows * C / 2;
+        const unsigned blocks = (unsigned)((pairs + 255) / 256);
+        if (bf16) pwv::k_planes_to_f32_n<true><<<blocks, 256, 0, st>>>(src, taps->layer_out, pairs, plane_elems);
+        else pwv::k_planes_to_f32_n<false><<<blocks, 256, 0, st>>>(src, taps->layer_out, pairs, plane_elems);
+        ++*launches;
+      }
+    }
+  }
+  {
+    using Cfg = pwv::TileCfg<C>;
+    const dim3 sgrid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
+    pwv::PostParams q;
+    q.z = w.act[cur];
+    for (int b = 0; b < 2; ++b) {
+      const BodyOff& bo = m->bodies[flow * 2 + b];
+      const LayerOff& lo = bo.layers[L - 1];
+      q.ws[b] = m->d_arena + lo.ws; q.bs[b] = m->d_arena + lo.bs;
+      q.w1[b] = m->d_arena + bo.w1; q.b1[b] = m->d_arena + bo.b1;
+      q.w2[b] = m->d_arena + bo.w2; q.b2[b] = m->d_arena + bo.b2;
+    }
+    q.y = w.ss; q.N = N; q.T = T;
+    q.skip_sum = nullptr;
+    pwv::k_post_simt<C><<<sgrid, Cfg::NT, Cfg::SMEM, st>>>(q);
+    ++*launches;
+  }
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
 extern "C" {
 
 int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, void* workspace,
@@ -1056,16 +1159,24 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     ++launches;
   }
 
-  CUtensorMap maps[2], maps_h[2];
-  const bool planes = hp.precision != PWV_PREC_FP32 && m->tc_path == 1;
+  CUtensorMap maps[2], maps_h[2], map_z;
+  const bool wide = hp.precision != PWV_PREC_FP32 && C != pwv::TC_C;
+  const bool planes = hp.precision != PWV_PREC_FP32 && (m->tc_path == 1 || wide);
   if (hp.precision != PWV_PREC_FP32) {
+    const bool bf = hp.precision == PWV_PREC_BF16;
     for (int b = 0; b < 2; ++b) {
-      rc = encode_act_map(&maps[b], w.act[b], N, T);
-      if (rc) return rc;
-      if (planes) {
-        rc = encode_plane_map(&maps_h[b], w.act[b], N, T, hp.precision == PWV_PREC_BF16 ? 1 : 2, hp.precision == PWV_PREC_BF16);
+      if (!wide) {
+        rc = encode_act_map(&maps[b], w.act[b], N, T);
         if (rc) return rc;
       }
+      if (planes) {
+        rc = encode_plane_map(&maps_h[b], w.act[b], N, T, bf ? 1 : 2, bf, C);
+        if (rc) return rc;
+      }
+    }
+    if (wide) {
+      rc = encode_plane_map(&map_z, w.zbuf, N, T, bf ? 1 : 2, bf, C);
+      if (rc) return rc;
     }
   }
 
@@ -1104,7 +1215,23 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       ++launches;
     }
     // front: IAF combine of the previous flow + causal layers
-    if (planes) {
+    if (wide) {
+      pwv::FrontWParams f;
+      f.x_prev = x_prev;
+      f.scale = i == 0 ? nullptr : w.ss;
+      f.shift = i == 0 ? nullptr : w.ss + (size_t)N * T;
+      f.x_new = w.x[xcur];
+      f.wc[0] = m->d_arena + m->bodies[i * 2 + 0].causal;
+      f.wc[1] = m->d_arena + m->bodies[i * 2 + 1].causal;
+      f.act = reinterpret_cast<uint16_t*>(w.act[cur]);
+      f.N = N; f.T = T; f.C = C;
+      const size_t total = (size_t)N * T * (C / 8);
+      if (hp.precision == PWV_PREC_BF16) pwv::k_front_w<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      else pwv::k_front_w<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      ++launches;
+      x_prev = w.x[xcur];
+      xcur ^= 1;
+    } else if (planes) {
       pwv::FrontHParams f;
       f.x_prev = x_prev;
       f.scale = i == 0 ? nullptr : w.ss;
@@ -1140,6 +1267,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       if (C == 64) rc = launch_layers_simt<64>(m, w, i, N, T, st, taps, &cur, &launches);
       else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
+    } else if (wide) {
+      if (C == 128) rc = launch_layers_w<128>(m, w, maps_h, map_z, i, N, T, st, taps, &cur, &launches);
+      else rc = launch_layers_w<256>(m, w, maps_h, map_z, i, N, T, st, taps, &cur, &launches);
     } else if (planes) {
       rc = launch_layers_h(m, w, maps_h, maps, i, N, T, st, taps, &cur, &launches);
     } else {

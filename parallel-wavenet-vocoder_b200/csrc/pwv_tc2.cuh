@@ -64,6 +64,8 @@ struct ThLayerParams {
   const int* done_in;
   int* done_out;
   int done_target;
+  // Measured and left off (profiles/r2_ab_layer_h.txt: no gain; with the MMA lock released between the halves the two
+  // slots' GEMMs interleave and the slots fall into lock-step, the effect DESIGN 4.1 describes for round 1):
   int split1;               // 1: GEMM1 starts on the x[t-d] half of K as soon as those columns are copied (the x[t] boxes land later)
   int split2;               // 1: GEMM2 starts on the first 16-channel chunk of each half of z while the gate computes the second
   long long* trace;
@@ -367,9 +369,11 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         th_ld_row64(stage + q * TH_BOX_BYTES, r, half * 4, v);
         tmem_st16((q ? tAlo : tAhi) + half * 16, v);
       }
-      tmem_wait_st();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->ax_ready[slot]);       // (the x[t-d] half of K: GEMM1 may start on it)
+      if (p.split1) {                           // the x[t-d] half of K is handed over on its own: GEMM1 may start on it
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->ax_ready[slot]);
+      }
       mbar_wait(&bars->y_full[slot], par);
 #pragma unroll
       for (int q = 0; q < P; ++q) {
@@ -378,6 +382,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
       tmem_wait_st();
       tc_fence_before_sync();
+      if (!p.split1) mbar_arrive(&bars->ax_ready[slot]);
       mbar_arrive(&bars->ay_ready[slot]);
     };
 
@@ -434,9 +439,12 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
             split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
             tmem_st8(tAhi + half * 16 + c * 8, hi);
             if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
-            tmem_wait_st();
-            tc_fence_before_sync();
-            mbar_arrive(c == 0 ? &bars->za_ready[slot] : &bars->zb_ready[slot]);
+            if (c == 1 || p.split2) {          // (without the GEMM2 split both halves are handed over together)
+              tmem_wait_st();
+              tc_fence_before_sync();
+              if (c == 0 || !p.split2) mbar_arrive(&bars->za_ready[slot]);
+              if (c == 1) mbar_arrive(&bars->zb_ready[slot]);
+            }
             if (p.z_out && t < p.T) {    // use_skip_connection (non-default): every layer's z feeds the skip sum (k_skip_simt)
               float4* zo = reinterpret_cast<float4*>(p.z_out + (((size_t)body * p.N + n) * p.T + t) * TC_C + half * 32 + c * 16);
 #pragma unroll

@@ -68,6 +68,65 @@ inline void tw_pack_stage(uint8_t* dst, const float* w, int ld, int k0, const in
     }
 }
 
+// Weight streams of a model with C = residual = dilation channels (multiple of 64), per (flow, body, layer) in that order:
+//   gate  stream: for every output block nb (64 gate channels: columns [f block | g block] of the packed [2C][2C] matrix) the
+//                 2C/64 K-stages in K order (x[t-d] channels, then x[t] channels), each [hi | lo] = 2 x 64 x 128 x 2 B
+//   dense stream: for every output block nb (64 residual channels) the C/64 K-stages, each 2 x 64 x 64 x 2 B
+//   vec         : [KF / s1, KG / s1, 1 / s2, 0 | dense bias (C floats)]
+struct TwModel {
+  uint8_t* d_gate = nullptr;
+  uint8_t* d_dense = nullptr;
+  float* d_vec = nullptr;
+  size_t gate_bytes = 0, dense_bytes = 0;     // per (flow, body, layer)
+  int vec_floats = 0;
+  int C = 0;
+};
+
+inline void tw_model_free(TwModel& t) {
+  if (t.d_gate) cudaFree(t.d_gate);
+  if (t.d_dense) cudaFree(t.d_dense);
+  if (t.d_vec) cudaFree(t.d_vec);
+  t = TwModel();
+}
+
+// precision: 1 = f16x3, 2 = bf16; layers in (flow, body, layer) order, sources as for tc_model_build (packed fp32 arena)
+inline const char* tw_model_build(TwModel& t, int precision, int C, const std::vector<TcLayerSrc>& layers) {
+  if (C % 64 != 0 || C < 64) return "wide tensor-core kernels need a channel count that is a multiple of 64";
+  const bool bf16 = precision == 2, split = precision == 1;
+  const int NB = C / 64, KBg = 2 * C / 64, KBd = C / 64;
+  const size_t gstage = 2 * 64 * 128 * 2, dstage = 2 * 64 * 64 * 2;
+  tw_model_free(t);
+  t.C = C;
+  t.gate_bytes = (size_t)NB * KBg * gstage;
+  t.dense_bytes = (size_t)NB * KBd * dstage;
+  t.vec_floats = 4 + C;
+  std::vector<uint8_t> hg(layers.size() * t.gate_bytes, 0), hd(layers.size() * t.dense_bytes, 0);
+  std::vector<float> hv(layers.size() * (size_t)t.vec_floats, 0.f);
+  std::vector<int> cols(128);
+  for (size_t i = 0; i < layers.size(); ++i) {
+    const float s1 = bf16 ? 1.f : tc_pow2_scale(layers[i].wfg, (size_t)2 * C * 2 * C);
+    const float s2 = bf16 ? 1.f : tc_pow2_scale(layers[i].wd, (size_t)C * C);
+    for (int nb = 0; nb < NB; ++nb) {
+      for (int c = 0; c < 64; ++c) { cols[c] = nb * 64 + c; cols[64 + c] = C + nb * 64 + c; }
+      for (int kb = 0; kb < KBg; ++kb)
+        tw_pack_stage(hg.data() + i * t.gate_bytes + ((size_t)nb * KBg + kb) * gstage, layers[i].wfg, 2 * C, kb * 64, cols.data(), 128, s1, bf16, split);
+      for (int kb = 0; kb < KBd; ++kb)
+        tw_pack_stage(hd.data() + i * t.dense_bytes + ((size_t)nb * KBd + kb) * dstage, layers[i].wd, C, kb * 64, cols.data(), 64, s2, bf16, split);
+    }
+    float* v = hv.data() + i * (size_t)t.vec_floats;
+    v[0] = TC_KF / s1; v[1] = TC_KG / s1; v[2] = 1.f / s2; v[3] = 0.f;
+    std::memcpy(v + 4, layers[i].bd, C * sizeof(float));
+  }
+  if (cudaMalloc(&t.d_gate, hg.size()) != cudaSuccess || cudaMalloc(&t.d_dense, hd.size()) != cudaSuccess ||
+      cudaMalloc(&t.d_vec, hv.size() * sizeof(float)) != cudaSuccess)
+    return "cudaMalloc of the wide tensor-core weight streams failed";
+  if (cudaMemcpy(t.d_gate, hg.data(), hg.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.d_dense, hd.data(), hd.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.d_vec, hv.data(), hv.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return "upload of the wide tensor-core weight streams failed";
+  return nullptr;
+}
+
 template <bool BF16, int EPI>
 __global__ void __launch_bounds__(TW_THREADS, 1)
 k_wide_h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_out, TwParams p) {

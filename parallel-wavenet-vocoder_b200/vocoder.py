@@ -36,8 +36,11 @@ def _assert_supported(hp):
 
 
 def tensor_core_covers(dims):
-    """Channel counts the tcgen05 kernels implement (csrc/pwv_tc2.cuh): R = D = 64, S = 128."""
-    return dims['R'] == 64 and dims['D'] == 64 and dims['S'] == 128
+    """Graphs the tcgen05 kernels implement: R = D = 64, S = 128 (csrc/pwv_tc2.cuh: the whole layer in one kernel) and
+    R = D in {128, 256}, S = 2R without skip connections (csrc/pwv_tc3.cuh: streamed-K gate and dense passes)."""
+    if dims['R'] != dims['D'] or dims['S'] != 2 * dims['R']:
+        return False
+    return dims['R'] == 64 or (dims['R'] in (128, 256) and not dims['use_skip'])
 
 
 def resolve_precision(dims, precision):
@@ -47,8 +50,9 @@ def resolve_precision(dims, precision):
         if tensor_core_covers(dims):
             return 'f16x3'
         import warnings
-        warnings.warn(f"engine.precision 'auto': residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} are outside the "
-                      f"tensor-core kernels' coverage (64/64/128); running the exact fp32 FFMA kernels", RuntimeWarning, stacklevel=2)
+        warnings.warn(f"engine.precision 'auto': residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} "
+                      f"(use_skip_connection={bool(dims['use_skip'])}) are outside the tensor-core kernels' coverage; "
+                      f"running the exact fp32 FFMA kernels", RuntimeWarning, stacklevel=2)
         return 'fp32'
     return precision
 

@@ -31,7 +31,7 @@ def _oracle(hp, weights, noise, mel, taps=None, fast=False):
 
 
 @pytest.mark.parametrize('channels,precision,debug', [(64, 'fp32', None), (128, 'fp32', None), (256, 'fp32', None), (64, 'f16x3', None),
-                                                      (64, 'f16x3', LEGACY)])
+                                                      (64, 'f16x3', LEGACY), (128, 'f16x3', None), (256, 'f16x3', None)])
 def test_small_against_oracle_with_taps(hp, channels, precision, debug):
     """Every debug tap against the oracle's: a gated layer's dense output, both WaveNet outputs of every flow
     (scale, shift: reference modules.py:56-57), x after every flow, the waveform."""
@@ -239,6 +239,29 @@ def test_other_conditioning_widths(hp, n_mels, cc, precision):
     ref = _oracle(hp, weights, noise, mel)
     out, _ = _run(hp, weights, noise, mel)
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize('channels', [128, 256])
+def test_wide_channels_on_tensor_cores(hp, channels):
+    """BASELINE config c5's channel counts (R = D = 128 / 256, S = 2R) on tcgen05 (k_wide_h: streamed-K gate and dense
+    passes): f16x3 within 1e-4 of the oracle on a 2-flow graph with a d >= T tap, ragged tiles and an odd batch; 'auto'
+    selects it; bit-exact determinism and batch independence; bf16 runs and its drift is bounded."""
+    small_case(hp, channels=channels, dilations=((1, 2, 512), (4, 1)), n=3, t=1040, precision='auto')
+    weights = pkg('weights').init_weights(hp, seed=17, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(3, 1040, 80, 80, mel_seed=5, noise_seed=6)
+    ref = _oracle(hp, weights, noise, mel)
+    out, model = _run(hp, weights, noise, mel)
+    assert model.precision == 'f16x3'
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(channels, 'channels f16x3 max|delta| =', err)
+    assert err <= TOL
+    dn, dm = torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()
+    assert torch.equal(model.forward(dn, dm), out)
+    assert torch.equal(model.forward(dn[1:2], dm[1:2])[0], out[1])
+    outb, _ = _run(hp, weights, noise, mel, precision='bf16')
+    errb = np.abs(outb.cpu().numpy() - ref).max()
+    print(channels, 'channels bf16 max|delta| =', errb)
+    assert np.isfinite(errb) and errb <= 6e-2 * max(1.0, float(np.abs(ref).max()))
 
 
 @pytest.mark.parametrize('channels', [64, 128])

@@ -5,10 +5,10 @@ For every (L, C) point: one flow (scaler + shifter bodies) with dilations = firs
 R = D = C, S = 2C, N*T >= 4M samples so the activations (>= 1 GB per buffer) cannot sit in L2. Reports
 the gated-layer kernel's device time per launch (CUDA events inside the library), algorithmic GB/s
 (2 bodies x N*T x 2*C*4 bytes per layer launch) against the measured HBM peak, and fp32-equivalent
-TFLOP/s. C = 64 runs on the tcgen05 path (f16x3) and the fp32 FFMA path; C = 128/256 on the FFMA path
-(the tensor-core kernels are C = 64 only).
+TFLOP/s. Every channel count runs on the tcgen05 path (f16x3: k_layer_h at C = 64, the streamed-K k_wide_h gate + dense
+passes at C = 128 / 256 -- there "layer_launch_us" is the time of a layer's two passes) and on the fp32 FFMA path.
 
-    python tools/sweep_c5.py [--quick] > profiles/r1_c5_sweep.json
+    python tools/sweep_c5.py [--quick] > profiles/r2_c5_sweep.jsonl
 """
 import argparse
 import importlib
@@ -40,7 +40,7 @@ def main():
     out = []
     for c in (64, 128, 256):
         for layers in (10, 20, 30):
-            for prec in (('f16x3', 'fp32') if c == 64 else ('fp32',)):
+            for prec in ('f16x3', 'fp32'):
                 hp.set_hparam_dict({'model': {'n_iaf': 1, 'dilations': [base[:layers]], 'residual_channels': c,
                                               'dilation_channels': c, 'skip_channels': 2 * c},
                                     'generate': {'batch_size': n, 'length': t}}, case='c5')
