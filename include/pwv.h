@@ -48,6 +48,8 @@ extern "C" {
 /* mel -> sample-rate conditioning (reference models.py:105-136) */
 #define PWV_UPSAMPLE_REPEAT 0            /* 1x1 conv + relu, every frame repeated hop times (default)       */
 #define PWV_UPSAMPLE_TRANSPOSED_CONV 1   /* stacked conv2d_transpose (kernel = stride) + relu per stage      */
+#define PWV_NORM_NONE 0
+#define PWV_NORM_IN 1
 
 /* error codes */
 #define PWV_OK 0
@@ -77,13 +79,18 @@ typedef struct pwv_hparams {
   int32_t n_mels;                 /* signal.n_mels                                             */
   int32_t hop_length;             /* signal.hop_length                                         */
   int32_t use_biases;             /* model.use_biases                                          */
-  int32_t use_skip_connection;    /* model.use_skip_connection; 1 needs precision PWV_PREC_FP32  */
+  int32_t use_skip_connection;    /* model.use_skip_connection                                    */
   int32_t precision;              /* PWV_PREC_*                                                */
   int32_t n_layers[PWV_MAX_FLOWS];                     /* len(model.dilations[i])              */
   int32_t dilations[PWV_MAX_FLOWS][PWV_MAX_LAYERS];    /* model.dilations[i][j]                */
   int32_t cond_upsample;          /* model.cond_upsample_method: PWV_UPSAMPLE_REPEAT | _TRANSPOSED_CONV  */
   int32_t n_upsample;             /* transposed_conv: number of stages (reference models.py:23: 3) ...   */
   int32_t upsample_strides[PWV_MAX_UPSAMPLE];  /* ... and their strides ([4,4,5]); product == hop_length  */
+  /* normalisers (reference modules.py:263-284): PWV_NORM_NONE ('' / None) or PWV_NORM_IN ('in': instance normalisation
+   * over time); 'bn' is tf.layers.batch_normalization and is not implemented. Any normaliser needs PWV_PREC_FP32. */
+  int32_t normalize;              /* model.normalize: x after every flow (models.py:70)                           */
+  int32_t normalize_cond;         /* model.normalize_cond: the conditioning (models.py:27-29,121-122)             */
+  int32_t normalize_wavenet;      /* model.normalize_wavenet: inside the WaveNet bodies (modules.py:149-257)      */
 } pwv_hparams;
 
 /* Optional debug taps for parity tests (all device pointers, any may be NULL). */

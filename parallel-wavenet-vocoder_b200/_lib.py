@@ -37,6 +37,7 @@ class PwvHparams(ctypes.Structure):
         ('dilations', (ctypes.c_int32 * PWV_MAX_LAYERS) * PWV_MAX_FLOWS),
         ('cond_upsample', ctypes.c_int32), ('n_upsample', ctypes.c_int32),
         ('upsample_strides', ctypes.c_int32 * PWV_MAX_UPSAMPLE),
+        ('normalize', ctypes.c_int32), ('normalize_cond', ctypes.c_int32), ('normalize_wavenet', ctypes.c_int32),
     ]
 
 
@@ -134,6 +135,12 @@ def make_hparams(dims, precision='fp32'):
     h.n_upsample = len(strides)
     for i, st in enumerate(strides):
         h.upsample_strides[i] = int(st)
+    for field, key in (('normalize', 'norm_flow'), ('normalize_cond', 'norm_cond'), ('normalize_wavenet', 'norm_wavenet')):
+        method = dims.get(key, '') or ''
+        if method not in ('', 'in'):
+            raise NotImplementedError(f"normaliser {method!r}: '' and 'in' (reference modules.py:274-284) are implemented; "
+                                      f"'bn' is tf.layers.batch_normalization")
+        setattr(h, field, 1 if method == 'in' else 0)
     if dims['n_iaf'] > PWV_MAX_FLOWS:
         raise ValueError(f'n_iaf {dims["n_iaf"]} > {PWV_MAX_FLOWS}')
     for i, dil in enumerate(dims['dilations']):

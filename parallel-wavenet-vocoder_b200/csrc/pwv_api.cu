@@ -20,6 +20,7 @@
 #include "pwv_tc2.cuh"
 #include "pwv_tc3.cuh"
 #include "pwv_mel.cuh"
+#include "pwv_norm.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -58,13 +59,19 @@ const char* kBodies[2] = {"scalar", "shifter"};   // reference models.py:48,63 (
 }  // namespace
 
 // per (flow, body) offsets (in floats) into the device weight arena
+struct NormOff {                 // instance-normalisation variables of one call site (gamma then beta), or npos when off
+  size_t gamma = (size_t)-1, beta = (size_t)-1;
+};
 struct LayerOff {
   size_t wfg, wd, bd, ws, bs;
+  NormOff n_fg;                  // [2C]: normalize_filter | normalize_gate (reference modules.py:230-234)
+  NormOff n_skip, n_dense;       // [S], [R] (modules.py:253-257)
 };
 struct BodyOff {
   size_t causal;                 // [2][C]
   std::vector<LayerOff> layers;
   size_t w1, b1, w2, b2;
+  NormOff n_causal, n_pp1, n_pp2;   // [R], [S], [S] (modules.py:181-182,149-151,158-160)
 };
 
 #ifndef PWV_TC_VARIANT_DEFAULT
@@ -91,6 +98,9 @@ struct pwv_model {
 
   // conditioning projections of a flow, contiguous so one batched GEMM covers them:
   // off_wgc[flow] -> [2 bodies][L][Cc][2C]  ([gc_filter | gc_gate]),  off_bfg[flow] -> [2][L][2C]
+  NormOff n_cond;                // [Cc] (models.py:27-29)
+  NormOff n_up[PWV_MAX_UPSAMPLE];   // [Cc] per transposed-conv stage (models.py:121-122)
+  std::vector<NormOff> n_flow;   // [1] per flow (models.py:70)
   std::vector<size_t> off_wgc, off_bfg;
   size_t off_colscale = 0;       // [2C]: -2log2e (filter half), -log2e (gate half) for the tensor-core epilogue
   int num_sms = 148;
@@ -159,20 +169,30 @@ static void build_var_list(pwv_model* m) {
   const pwv_hparams& hp = m->hp;
   const int64_t k = hp.filter_width, R = hp.residual_channels, D = hp.dilation_channels,
                 S = hp.skip_channels, Cc = hp.condition_channels;
+  // instance_normalization creates beta before gamma (reference modules.py:279-280)
+  auto norm = [&](const std::string& scope, int64_t channels, bool on) {
+    if (!on) return;
+    add_var(m, scope + "/beta", {channels});
+    add_var(m, scope + "/gamma", {channels});
+  };
+  const bool nc = hp.normalize_cond == PWV_NORM_IN, nw = hp.normalize_wavenet == PWV_NORM_IN, nf = hp.normalize == PWV_NORM_IN;
   if (hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
     // reference models.py:109-124: w_i [1, stride_i, Cc (out), Cin]; Cin = n_mels for stage 0, Cc afterwards
     int64_t cin = hp.n_mels;
     for (int i = 0; i < hp.n_upsample; ++i) {
       add_var(m, "iaf_vocoder/cond/transposed_conv_" + std::to_string(i) + "_weights", {1, hp.upsample_strides[i], Cc, cin});
+      norm("iaf_vocoder/cond/normalize_transposed_conv_" + std::to_string(i), Cc, nc);
       cin = Cc;
     }
   } else {
     add_var(m, "iaf_vocoder/cond/dense", {1, hp.n_mels, Cc});
   }
-  for (int i = 0; i < hp.n_iaf; ++i)
+  norm("iaf_vocoder/cond/normalize/normalize", Cc, nc);
+  for (int i = 0; i < hp.n_iaf; ++i) {
     for (int b = 0; b < 2; ++b) {
       std::string p = "iaf_vocoder/iaf" + std::to_string(i) + "/" + kBodies[b];
       add_var(m, p + "/causal_layer/filter", {k, 1, R});
+      norm(p + "/causal_layer/normalize", R, nw);
       for (int j = 0; j < hp.n_layers[i]; ++j) {
         std::string q = p + "/dilated_stack/layer" + std::to_string(j);
         add_var(m, q + "/filter", {k, R, D});
@@ -183,19 +203,27 @@ static void build_var_list(pwv_model* m) {
           add_var(m, q + "/filter_bias", {D});
           add_var(m, q + "/gate_bias", {D});
         }
+        norm(q + "/normalize_filter", D, nw);
+        norm(q + "/normalize_gate", D, nw);
         add_var(m, q + "/dense", {1, D, R});
         add_var(m, q + "/skip", {1, D, S});
         if (hp.use_biases) {
           add_var(m, q + "/dense_bias", {R});
           add_var(m, q + "/skip_bias", {S});
         }
+        norm(q + "/normalize_skip_output", S, nw);
+        norm(q + "/normalize_dense_output", R, nw);
       }
       std::string q = p + "/postprocessing";
+      norm(q + "/normalize_postprocess1", S, nw);
       add_var(m, q + "/postprocess1", {1, S, S});
       if (hp.use_biases) add_var(m, q + "/postprocess1_bias", {S});
+      norm(q + "/normalize_postprocess2", S, nw);
       add_var(m, q + "/postprocess2", {1, S, 1});
       if (hp.use_biases) add_var(m, q + "/postprocess2_bias", {1});
     }
+    norm("iaf_vocoder/normalize" + std::to_string(i), 1, nf);
+  }
   m->staged.resize(m->vars.size());
   m->loaded.assign(m->vars.size(), 0);
 }
@@ -289,6 +317,10 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   }
   if (hp->precision != PWV_PREC_FP32 && hp->precision != PWV_PREC_F16X3 && hp->precision != PWV_PREC_BF16)
     return fail(PWV_EINVAL, "unknown precision %d", hp->precision);
+  for (int v : {hp->normalize, hp->normalize_cond, hp->normalize_wavenet})
+    if (v != PWV_NORM_NONE && v != PWV_NORM_IN) return fail(PWV_EINVAL, "unknown normaliser %d (PWV_NORM_NONE or PWV_NORM_IN)", v);
+  if ((hp->normalize || hp->normalize_cond || hp->normalize_wavenet) && hp->precision != PWV_PREC_FP32)
+    return fail(PWV_EINVAL, "the 'in' normalisers run on the fp32 path only (precision fp32): a statistic over the whole time axis sits between the stages of a layer");
   if (hp->precision != PWV_PREC_FP32 && C != 64 && hp->use_skip_connection)
     return fail(PWV_EINVAL, "use_skip_connection=True at %d channels runs on the fp32 path only (precision fp32)", C);
   int total = 0, mx = 0;
@@ -391,6 +423,25 @@ int pwv_model_finalize(pwv_model* m) {
     arena[m->off_colscale + c] = pwv::TC_KF;
     arena[m->off_colscale + C + c] = pwv::TC_KG;
   }
+  auto put_norm = [&](const std::string& scope, size_t n) {     // gamma then beta, n floats each
+    NormOff o;
+    o.gamma = put(n);
+    o.beta = put(n);
+    const auto& g = var(m, scope + "/gamma");
+    const auto& b = var(m, scope + "/beta");
+    std::copy(g.begin(), g.end(), arena.begin() + o.gamma);
+    std::copy(b.begin(), b.end(), arena.begin() + o.beta);
+    return o;
+  };
+  const bool nrm_c = hp.normalize_cond == PWV_NORM_IN, nrm_w = hp.normalize_wavenet == PWV_NORM_IN, nrm_f = hp.normalize == PWV_NORM_IN;
+  if (nrm_c) {
+    m->n_cond = put_norm("iaf_vocoder/cond/normalize/normalize", Cc);
+    if (hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV)
+      for (int i = 0; i < hp.n_upsample; ++i) m->n_up[i] = put_norm("iaf_vocoder/cond/normalize_transposed_conv_" + std::to_string(i), Cc);
+  }
+  m->n_flow.assign(hp.n_iaf, NormOff());
+  if (nrm_f)
+    for (int i = 0; i < hp.n_iaf; ++i) m->n_flow[i] = put_norm("iaf_vocoder/normalize" + std::to_string(i), 1);
   m->bodies.assign(hp.n_iaf * 2, BodyOff());
   m->off_wgc.assign(hp.n_iaf, 0);
   m->off_bfg.assign(hp.n_iaf, 0);
@@ -405,10 +456,24 @@ int pwv_model_finalize(pwv_model* m) {
         const auto& w = var(m, p + "/causal_layer/filter");   // [2][1][C]
         std::copy(w.begin(), w.end(), arena.begin() + bo.causal);
       }
+      if (nrm_w) bo.n_causal = put_norm(p + "/causal_layer/normalize", C);
       bo.layers.resize(hp.n_layers[i]);
       for (int j = 0; j < hp.n_layers[i]; ++j) {
         LayerOff& lo = bo.layers[j];
         std::string q = p + "/dilated_stack/layer" + std::to_string(j);
+        if (nrm_w) {
+          lo.n_fg.gamma = put(2 * C);          // [filter | gate] halves side by side, like the pre-activation rows
+          lo.n_fg.beta = put(2 * C);
+          const char* part[2] = {"/normalize_filter", "/normalize_gate"};
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const auto& g = var(m, q + part[h2] + "/gamma");
+            const auto& bt = var(m, q + part[h2] + "/beta");
+            std::copy(g.begin(), g.end(), arena.begin() + lo.n_fg.gamma + h2 * C);
+            std::copy(bt.begin(), bt.end(), arena.begin() + lo.n_fg.beta + h2 * C);
+          }
+          lo.n_skip = put_norm(q + "/normalize_skip_output", S);
+          lo.n_dense = put_norm(q + "/normalize_dense_output", C);
+        }
         const auto& wf = var(m, q + "/filter");      // [2][C][C]
         const auto& wg = var(m, q + "/gate");
         lo.wfg = put((size_t)2 * C * 2 * C);
@@ -450,6 +515,10 @@ int pwv_model_finalize(pwv_model* m) {
         }
       }
       std::string q = p + "/postprocessing";
+      if (nrm_w) {
+        bo.n_pp1 = put_norm(q + "/normalize_postprocess1", S);
+        bo.n_pp2 = put_norm(q + "/normalize_postprocess2", S);
+      }
       bo.w1 = put((size_t)S * S);
       bo.b1 = put(S);
       bo.w2 = put(S);
@@ -541,6 +610,10 @@ struct Workspace {
   float* x[2];      // [N][T] ping/pong
   float* zbuf;      // use_skip_connection: [2][N][T][C] gate output of the current layer
   float* skip;      // use_skip_connection: [2][N][T][2C] running sum of the skip outputs
+  float* fg;        // normalize_wavenet: [2][N][T][2C] pre-activations of the current layer
+  float* hbuf;      // normalize_wavenet: [2][N][T][2C] post-net hidden layer
+  float* total;     // normalize_wavenet + use_skip_connection: [2][N][T][2C] running sum of the normalised skip outputs
+  float2* stats;    // any normaliser: (mean, sqrt(var + eps)) per (utterance-body, channel)
   int* flags;       // tensor-core path: [total gated layers][2][N * ceil(T/128)] per-tile "output stored" flags
   size_t flags_bytes;
   size_t bytes;
@@ -548,15 +621,17 @@ struct Workspace {
 
 // Conditioning rows per utterance and samples per row: 'repeat' keeps the per-layer conditioning terms at mel
 // rate (row = frame (s + hop/2) / hop); 'transposed_conv' produces a different vector for every sample.
-static int cond_rows(const pwv_model* m, int T) {
-  return m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV ? T : 1 + T / m->hp.hop_length;
+// (a normalised conditioning is a per-sample tensor too: its statistics run over the repeated, cropped frames)
+static bool cond_full_rate(const pwv_model* m) {
+  return m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV || m->hp.normalize_cond == PWV_NORM_IN;
 }
-static int cond_hop(const pwv_model* m) { return m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV ? 1 : m->hp.hop_length; }
+static int cond_rows(const pwv_model* m, int T) { return cond_full_rate(m) ? T : 1 + T / m->hp.hop_length; }
+static int cond_hop(const pwv_model* m) { return cond_full_rate(m) ? 1 : m->hp.hop_length; }
 
 static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   const int C = m->C, t_mel = 1 + T / m->hp.hop_length;
   const bool tconv = m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV;
-  const size_t crows = tconv ? (size_t)T : (size_t)t_mel;     // conditioning rows per utterance (cond_rows)
+  const size_t crows = (size_t)cond_rows(m, T);               // conditioning rows per utterance
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
@@ -574,18 +649,33 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
     }
     w->up[0] = (float*)take(sizeof(float) * big[0] * m->Cc);
     w->up[1] = (float*)take(sizeof(float) * (big[1] ? big[1] : 1) * m->Cc);
+  } else if (m->hp.normalize_cond == PWV_NORM_IN) {
+    w->up[0] = (float*)take(sizeof(float) * (size_t)N * t_mel * m->Cc);   // mel-rate rows before the repeat is materialised
   }
   w->act[0] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
   w->act[1] = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
   w->ss = (float*)take(sizeof(float) * (size_t)2 * N * T);
   w->x[0] = (float*)take(sizeof(float) * (size_t)N * T);
   w->x[1] = (float*)take(sizeof(float) * (size_t)N * T);
-  w->zbuf = w->skip = nullptr;
-  if (m->hp.use_skip_connection) {
+  w->zbuf = w->skip = w->fg = w->hbuf = w->total = nullptr;
+  w->stats = nullptr;
+  if (m->hp.normalize_wavenet == PWV_NORM_IN) {
+    const size_t S = (size_t)m->S;
+    w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
+    w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
+    w->fg = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
+    w->hbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
+    if (m->hp.use_skip_connection) w->total = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
+  } else if (m->hp.use_skip_connection) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
     w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
   } else if (m->hp.precision != PWV_PREC_FP32 && C != pwv::TC_C) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);     // z planes between the gate and the dense pass (k_wide_h)
+  }
+  if (m->hp.normalize || m->hp.normalize_cond || m->hp.normalize_wavenet) {
+    size_t widest = (size_t)2 * N * (2 * C > m->S ? 2 * C : m->S);
+    if ((size_t)N * m->Cc > widest) widest = (size_t)N * m->Cc;
+    w->stats = (float2*)take(sizeof(float2) * widest);
   }
   w->flags = nullptr;
   w->flags_bytes = 0;
@@ -629,6 +719,115 @@ static int launch_cond_gemm(int C, const float* A, const pwv::RowGemmBatch& rb, 
   if (C == 64) return launch_cond_gemm_c<64>(A, rb, M, K, Z, st);
   if (C == 128) return launch_cond_gemm_c<128>(A, rb, M, K, Z, st);
   return launch_cond_gemm_c<256>(A, rb, M, K, Z, st);
+}
+
+
+// x [UB][T][Cn] normalised in place over time (pwv_norm.cuh); groups of `ub_per_group` utterance-bodies use (g0, b0), the rest (g1, b1)
+static int launch_in_norm(const pwv_model* m, const Workspace& w, float* x, int UB, int T, int Cn, const NormOff& a, const NormOff& b,
+                          int ub_per_group, bool pre_relu, cudaStream_t st, int* launches) {
+  const dim3 sgrid((Cn + 31) / 32, UB);
+  const size_t total = (size_t)UB * T * Cn;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const float *g0 = m->d_arena + a.gamma, *b0 = m->d_arena + a.beta, *g1 = m->d_arena + b.gamma, *b1 = m->d_arena + b.beta;
+  if (pre_relu) {
+    pwv::k_in_stats<true><<<sgrid, 256, 0, st>>>(x, w.stats, T, Cn);
+    pwv::k_in_apply<true><<<blocks, 256, 0, st>>>(x, w.stats, g0, b0, g1, b1, ub_per_group, (size_t)T * Cn, Cn, total);
+  } else {
+    pwv::k_in_stats<false><<<sgrid, 256, 0, st>>>(x, w.stats, T, Cn);
+    pwv::k_in_apply<false><<<blocks, 256, 0, st>>>(x, w.stats, g0, b0, g1, b1, ub_per_group, (size_t)T * Cn, Cn, total);
+  }
+  *launches += 2;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
+// One flow's WaveNet bodies with normalize_wavenet = 'in' (reference modules.py:129-259 with self.normalize set): every
+// normalised tensor is materialised, so a layer is pre-activations -> norm -> gate + dense (+ z) -> norm (-> skip -> norm).
+template <int C>
+static int launch_layers_in(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st, const pwv_taps* taps,
+                            int* cur_buf, int* launches) {
+  using Cfg = pwv::TileCfg<C>;
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], t_mel = cond_rows(m, T), c_hop = cond_hop(m), S = m->S;
+  const dim3 grid((T + Cfg::TM - 1) / Cfg::TM, N, 2);
+  const size_t rows = (size_t)N * T;
+  const BodyOff& b0 = m->bodies[flow * 2 + 0];
+  const BodyOff& b1 = m->bodies[flow * 2 + 1];
+  int cur = *cur_buf, rc;
+  rc = launch_in_norm(m, w, w.act[cur], 2 * N, T, C, b0.n_causal, b1.n_causal, N, false, st, launches);   // modules.py:181-182
+  if (rc) return rc;
+  for (int j = 0; j < L; ++j) {
+    const bool last = j == L - 1;
+    const LayerOff& l0 = b0.layers[j];
+    const LayerOff& l1 = b1.layers[j];
+    pwv::LayerParams p;
+    p.x_in = w.act[cur];
+    p.x_out = w.act[cur ^ 1];
+    for (int b = 0; b < 2; ++b) {
+      const LayerOff& lo = m->bodies[flow * 2 + b].layers[j];
+      p.wfg[b] = m->d_arena + lo.wfg;
+      p.wd[b] = m->d_arena + lo.wd;
+      p.bd[b] = m->d_arena + lo.bd;
+      p.cbias[b] = w.cbias + ((size_t)b * L + j) * N * t_mel * 2 * C;
+    }
+    p.N = N; p.T = T; p.t_mel = t_mel; p.hop = c_hop; p.dilation = hp.dilations[flow][j];
+    p.z_out = w.zbuf; p.fg_out = w.fg; p.fg_in = w.fg;
+    PWV_PROF_MARK(m, st);
+    p.mode = 3;                                                                   // [f|g] incl. conditioning and biases
+    pwv::k_layer_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    ++*launches;
+    rc = launch_in_norm(m, w, w.fg, 2 * N, T, 2 * C, l0.n_fg, l1.n_fg, N, false, st, launches);            // modules.py:230-234
+    if (rc) return rc;
+    p.mode = 4;                                                                   // gate, dense 1x1, residual; z kept for the skip
+    pwv::k_layer_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    ++*launches;
+    cur ^= 1;
+    rc = launch_in_norm(m, w, w.act[cur], 2 * N, T, C, l0.n_dense, l1.n_dense, N, false, st, launches);    // modules.py:256-257
+    if (rc) return rc;
+    if (hp.use_skip_connection || last) {                                          // skip_output (dead otherwise), modules.py:243-255
+      pwv::SkipParams sp;
+      sp.z = w.zbuf;
+      sp.ws[0] = m->d_arena + l0.ws; sp.bs[0] = m->d_arena + l0.bs;
+      sp.ws[1] = m->d_arena + l1.ws; sp.bs[1] = m->d_arena + l1.bs;
+      sp.skip_sum = w.skip; sp.N = N; sp.T = T; sp.first = 1;
+      pwv::k_skip_simt<C><<<grid, Cfg::NT, Cfg::SMEM, st>>>(sp);
+      ++*launches;
+      rc = launch_in_norm(m, w, w.skip, 2 * N, T, S, l0.n_skip, l1.n_skip, N, false, st, launches);
+      if (rc) return rc;
+      if (hp.use_skip_connection) {                                                // sum(outputs), modules.py:147
+        const size_t n = 2 * rows * S;
+        if (j == 0) PWV_CUDA(cudaMemcpyAsync(w.total, w.skip, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+        else { pwv::k_add_inplace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.total, w.skip, n); ++*launches; }
+      }
+    }
+    PWV_PROF_MARK(m, st);
+    if (m->profiling) ++m->prof_launches;
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
+      PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * rows * C, sizeof(float) * rows * C, cudaMemcpyDeviceToDevice, st));
+  }
+  // post-net: relu -> norm -> 1x1 + bias -> relu -> norm -> 1x1 + bias (modules.py:148-165)
+  float* src = hp.use_skip_connection ? w.total : w.skip;
+  rc = launch_in_norm(m, w, src, 2 * N, T, S, b0.n_pp1, b1.n_pp1, N, true, st, launches);
+  if (rc) return rc;
+  for (int b = 0; b < 2; ++b) {
+    const BodyOff& bo = m->bodies[flow * 2 + b];
+    pwv::RowGemmBatch rb{m->d_arena + bo.w1, 0, m->d_arena + bo.b1, 0, w.hbuf + (size_t)b * rows * S, 0, nullptr};
+    dim3 g((S + 63) / 64, (unsigned)((rows + 63) / 64), 1);
+    pwv::k_row_gemm<true><<<g, 256, 0, st>>>(src + (size_t)b * rows * S, rb, (int)rows, S, S);
+    ++*launches;
+  }
+  rc = launch_in_norm(m, w, w.hbuf, 2 * N, T, S, b0.n_pp2, b1.n_pp2, N, false, st, launches);
+  if (rc) return rc;
+  for (int b = 0; b < 2; ++b) {
+    const BodyOff& bo = m->bodies[flow * 2 + b];
+    pwv::RowGemmBatch rb{m->d_arena + bo.w2, 0, m->d_arena + bo.b2, 0, w.ss + (size_t)b * rows, 0, nullptr};
+    dim3 g(1, (unsigned)((rows + 63) / 64), 1);
+    pwv::k_row_gemm<false><<<g, 256, 0, st>>>(w.hbuf + (size_t)b * rows * S, rb, (int)rows, S, 1);
+    ++*launches;
+  }
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
 }
 
 template <int C>
@@ -1145,6 +1344,13 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       src = dst;
       rows *= hp.upsample_strides[i];
       cin = Cc;
+      if (hp.normalize_cond == PWV_NORM_IN) {
+        // reference models.py:121-122 normalises the 4-D tensor (n, 1, len, C) over its size-1 axis (modules.py:277):
+        // mean = x, variance = 0, so the stage's output is its beta, whatever the input (replayed literally)
+        const size_t n_el = (size_t)rows * Cc;
+        pwv::k_fill_rows<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(dst, m->d_arena + m->n_up[i].beta, (size_t)rows, Cc);
+        ++launches;
+      }
     }
     // crop: utterance n keeps rows hop/2 .. hop/2 + T - 1 of its t_mel * hop upsampled rows
     PWV_CUDA(cudaMemcpy2DAsync(w.cproj, sizeof(float) * (size_t)T * Cc, src + (size_t)(hp.hop_length / 2) * Cc,
@@ -1152,11 +1358,21 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
                                cudaMemcpyDeviceToDevice, st));
   } else {
     // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
-    pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, w.cproj, 0, nullptr};
+    const bool full = hp.normalize_cond == PWV_NORM_IN;       // then the repeated, cropped rows are materialised for the statistics
+    pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, full ? w.up[0] : w.cproj, 0, nullptr};
     const int M = N * t_mel;
     dim3 grid((Cc + 63) / 64, (M + 63) / 64, 1);
     pwv::k_row_gemm<true><<<grid, 256, 0, st>>>(mel, rb, M, hp.n_mels, Cc);
     ++launches;
+    if (full) {
+      const size_t n_el = (size_t)N * T * Cc;
+      pwv::k_repeat_crop<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(w.up[0], w.cproj, N, T, t_mel, hp.hop_length, Cc);
+      ++launches;
+    }
+  }
+  if (hp.normalize_cond == PWV_NORM_IN) {                       // models.py:27-29, after the crop
+    rc = launch_in_norm(m, w, w.cproj, N, T, Cc, m->n_cond, m->n_cond, N, false, st, &launches);
+    if (rc) return rc;
   }
 
   CUtensorMap maps[2], maps_h[2], map_z;
@@ -1182,6 +1398,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
 
   int cur = 0, xcur = 0;
   const float* x_prev = noise;
+  const bool nrm_f = hp.normalize == PWV_NORM_IN;     // x is combined and normalised explicitly after every flow
+  if (hp.normalize_wavenet == PWV_NORM_IN && ((size_t)N * T + 63) / 64 > 65535)
+    return fail(PWV_EINVAL, "normalize_wavenet: N*T = %zu exceeds the un-fused post-net's grid (4,194,240 samples per call)", (size_t)N * T);
   for (int i = 0; i < hp.n_iaf; ++i) {
     const int L = hp.n_layers[i];
     // per-layer conditioning terms of this flow: cbias[b][j] = cproj . [gc_filter|gc_gate] + [bf|bg]
@@ -1250,8 +1469,8 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     } else {
       pwv::FrontParams f;
       f.x_prev = x_prev;
-      f.scale = i == 0 ? nullptr : w.ss;
-      f.shift = i == 0 ? nullptr : w.ss + (size_t)N * T;
+      f.scale = (i == 0 || nrm_f) ? nullptr : w.ss;
+      f.shift = (i == 0 || nrm_f) ? nullptr : w.ss + (size_t)N * T;
       f.x_new = w.x[xcur];
       f.wc[0] = m->d_arena + m->bodies[i * 2 + 0].causal;
       f.wc[1] = m->d_arena + m->bodies[i * 2 + 1].causal;
@@ -1263,7 +1482,11 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       x_prev = w.x[xcur];
       xcur ^= 1;
     }
-    if (hp.precision == PWV_PREC_FP32) {
+    if (hp.normalize_wavenet == PWV_NORM_IN) {
+      if (C == 64) rc = launch_layers_in<64>(m, w, i, N, T, st, taps, &cur, &launches);
+      else if (C == 128) rc = launch_layers_in<128>(m, w, i, N, T, st, taps, &cur, &launches);
+      else rc = launch_layers_in<256>(m, w, i, N, T, st, taps, &cur, &launches);
+    } else if (hp.precision == PWV_PREC_FP32) {
       if (C == 64) rc = launch_layers_simt<64>(m, w, i, N, T, st, taps, &cur, &launches);
       else if (C == 128) rc = launch_layers_simt<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_simt<256>(m, w, i, N, T, st, taps, &cur, &launches);
@@ -1278,13 +1501,25 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
     if (rc) return rc;
     if (taps && taps->scale_shift)
       PWV_CUDA(cudaMemcpyAsync(taps->scale_shift + (size_t)i * 2 * N * T, w.ss, sizeof(float) * 2 * (size_t)N * T, cudaMemcpyDeviceToDevice, st));
-    if (taps && taps->flow_out) {
+    if (nrm_f) {        // x = x * scale + shift (modules.py:57-59), then normalize{i} over time (models.py:70)
+      const size_t n = (size_t)N * T;
+      float* xn = w.x[xcur];
+      pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, xn, n);
+      ++launches;
+      rc = launch_in_norm(m, w, xn, N, T, 1, m->n_flow[i], m->n_flow[i], N, false, st, &launches);
+      if (rc) return rc;
+      x_prev = xn;
+      xcur ^= 1;
+      if (taps && taps->flow_out) PWV_CUDA(cudaMemcpyAsync(taps->flow_out + (size_t)i * n, xn, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    } else if (taps && taps->flow_out) {
       const size_t n = (size_t)N * T;
       pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, taps->flow_out + (size_t)i * n, n);
       ++launches;
     }
   }
-  {
+  if (nrm_f) {
+    PWV_CUDA(cudaMemcpyAsync(wav, x_prev, sizeof(float) * (size_t)N * T, cudaMemcpyDeviceToDevice, st));
+  } else {
     const size_t n = (size_t)N * T;
     pwv::k_iaf_combine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_prev, w.ss, w.ss + n, wav, n);
     ++launches;

@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_cond_gemm(const float* __res
 //                                                 post-net kernel consumes z)
 //   mode 2: mode 0 + z_out[t] = z                (use_skip_connection: every layer's skip output
 //                                                 is needed, k_skip_simt consumes z)
+//   mode 3: fg_out[t] = [f|g] and stop           (normalize_wavenet: the pre-activations are normalised over the
+//                                                 whole time axis before the gate, pwv_norm.cuh)
+//   mode 4: [f|g] = fg_in[t] (already normalised), then as mode 2
 // grid = (ceil(T/TM), N, 2 bodies)
 // ------------------------------------------------------------------------------------------------
 struct LayerParams {
@@ -306,7 +309,9 @@ struct LayerParams {
   const float* wd[2];     // [C][C]
   const float* bd[2];     // [C]
   const float* cbias[2];  // [N][t_mel][2C]
-  float* z_out;           // [2][N][T][C], mode 2 only
+  float* z_out;           // [2][N][T][C], modes 2 and 4
+  float* fg_out;          // [2][N][T][2C], mode 3
+  const float* fg_in;     // [2][N][T][2C], mode 4
   int N, T, t_mel, hop, dilation, mode;
 };
 
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_layer_simt(LayerParams p) {
   float* __restrict__ xout = p.x_out + body * body_stride + (size_t)n * p.T * C;
 
   // A tile: columns [0,C) = x[t-d], [C,2C) = x[t]; rows past T or before 0 are zero.
-  {
+  if (p.mode != 4) {
     constexpr int V = 2 * C / 4;   // float4 per row
     for (int e = threadIdx.x; e < TM * V; e += NT) {
       const int m = e / V, v = e % V;
@@ -343,33 +348,49 @@ __global__ void __launch_bounds__(TileCfg<C>::NT) k_layer_simt(LayerParams p) {
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  tile_gemm<NTX, NTY, 8>(As, LDA, 2 * C, p.wfg[body], 2 * C, Bs, acc);
+  if (p.mode != 4) tile_gemm<NTX, NTY, 8>(As, LDA, 2 * C, p.wfg[body], 2 * C, Bs, acc);
 
   // conditioning term + gate; z tile aliases the A tile (tile_gemm ended with a barrier)
   float* Zs = As;                   // [TM][C+4]
   constexpr int LDZ = C + 4;
   const float* __restrict__ cb = p.cbias[body] + (size_t)n * p.t_mel * 2 * C;
+  const size_t fg_base = ((size_t)body * p.N + n) * p.T * 2 * C;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = ty + NTY * i;
     const int t = min(t0 + m, p.T - 1);
-    const int frame = (t + p.hop / 2) / p.hop;
-    const float4 cf = *reinterpret_cast<const float4*>(cb + (size_t)frame * 2 * C + 4 * tx);
-    const float4 cg = *reinterpret_cast<const float4*>(cb + (size_t)frame * 2 * C + C + 4 * tx);
+    float4 f, g;
+    if (p.mode == 4) {              // normalised pre-activations from the previous pass
+      f = *reinterpret_cast<const float4*>(p.fg_in + fg_base + (size_t)t * 2 * C + 4 * tx);
+      g = *reinterpret_cast<const float4*>(p.fg_in + fg_base + (size_t)t * 2 * C + C + 4 * tx);
+    } else {
+      const int frame = (t + p.hop / 2) / p.hop;
+      const float4 cf = *reinterpret_cast<const float4*>(cb + (size_t)frame * 2 * C + 4 * tx);
+      const float4 cg = *reinterpret_cast<const float4*>(cb + (size_t)frame * 2 * C + C + 4 * tx);
+      f = make_float4(acc[i][0] + cf.x, acc[i][1] + cf.y, acc[i][2] + cf.z, acc[i][3] + cf.w);
+      g = make_float4(acc[i][4] + cg.x, acc[i][5] + cg.y, acc[i][6] + cg.z, acc[i][7] + cg.w);
+    }
+    if (p.mode == 3) {
+      if (t0 + m < p.T) {
+        *reinterpret_cast<float4*>(p.fg_out + fg_base + (size_t)(t0 + m) * 2 * C + 4 * tx) = f;
+        *reinterpret_cast<float4*>(p.fg_out + fg_base + (size_t)(t0 + m) * 2 * C + C + 4 * tx) = g;
+      }
+      continue;
+    }
     float4 z;
-    z.x = tanhf(acc[i][0] + cf.x) * sigmoid_exact(acc[i][4] + cg.x);
-    z.y = tanhf(acc[i][1] + cf.y) * sigmoid_exact(acc[i][5] + cg.y);
-    z.z = tanhf(acc[i][2] + cf.z) * sigmoid_exact(acc[i][6] + cg.z);
-    z.w = tanhf(acc[i][3] + cf.w) * sigmoid_exact(acc[i][7] + cg.w);
+    z.x = tanhf(f.x) * sigmoid_exact(g.x);
+    z.y = tanhf(f.y) * sigmoid_exact(g.y);
+    z.z = tanhf(f.z) * sigmoid_exact(g.z);
+    z.w = tanhf(f.w) * sigmoid_exact(g.w);
     if (p.mode == 1) {
       if (t0 + m < p.T) *reinterpret_cast<float4*>(xout + (size_t)(t0 + m) * C + 4 * tx) = z;
     } else {
       *reinterpret_cast<float4*>(Zs + (size_t)m * LDZ + 4 * tx) = z;
-      if (p.mode == 2 && t0 + m < p.T)
+      if ((p.mode == 2 || p.mode == 4) && t0 + m < p.T)
         *reinterpret_cast<float4*>(p.z_out + body * body_stride + ((size_t)n * p.T + t0 + m) * C + 4 * tx) = z;
     }
   }
-  if (p.mode == 1) return;
+  if (p.mode == 1 || p.mode == 3) return;
 
   float acc2[8][4];
 #pragma unroll

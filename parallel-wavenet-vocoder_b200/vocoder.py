@@ -23,9 +23,9 @@ from .hparam import hparam as hp
 def _assert_supported(hp):
     m = hp.model
     for key in ('normalize', 'normalize_cond', 'normalize_wavenet'):
-        if m.get(key):
-            raise NotImplementedError(f"model.{key}={m[key]!r}: normalisers are not on the B200 path "
-                                      f"(reference modules.py:263-284); they must be ''")
+        if m.get(key) and m[key] != 'in':
+            raise NotImplementedError(f"model.{key}={m[key]!r}: '' and 'in' (instance normalisation over time, reference "
+                                      f"modules.py:274-284) are on the B200 path; 'bn' (tf.layers.batch_normalization) is not")
     if m.cond_upsample_method not in ('repeat', 'transposed_conv'):
         # the reference then conditions on nothing (models.py:134-135: cond = None)
         raise NotImplementedError(f"model.cond_upsample_method={m.cond_upsample_method!r}: 'repeat' "
@@ -40,6 +40,8 @@ def tensor_core_covers(dims):
     R = D in {128, 256}, S = 2R without skip connections (csrc/pwv_tc3.cuh: streamed-K gate and dense passes)."""
     if dims['R'] != dims['D'] or dims['S'] != 2 * dims['R']:
         return False
+    if dims.get('norm_flow') or dims.get('norm_cond') or dims.get('norm_wavenet'):
+        return False                # a statistic over the whole time axis sits between the stages: un-fused fp32 kernels
     return dims['R'] == 64 or (dims['R'] in (128, 256) and not dims['use_skip'])
 
 
@@ -51,7 +53,8 @@ def resolve_precision(dims, precision):
             return 'f16x3'
         import warnings
         warnings.warn(f"engine.precision 'auto': residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} "
-                      f"(use_skip_connection={bool(dims['use_skip'])}) are outside the tensor-core kernels' coverage; "
+                      f"(use_skip_connection={bool(dims['use_skip'])}, normalisers {dims.get('norm_flow')!r}/{dims.get('norm_cond')!r}/"
+                      f"{dims.get('norm_wavenet')!r}) are outside the tensor-core kernels' coverage; "
                       f"running the exact fp32 FFMA kernels", RuntimeWarning, stacklevel=2)
         return 'fp32'
     return precision

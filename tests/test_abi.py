@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_hparams_struct_matches_header():
     L = pkg('_lib')
-    # 11 scalars + 8 + 8*64 int32, then cond_upsample, n_upsample, upsample_strides[4]
-    assert ctypes.sizeof(L.PwvHparams) == 4 * (11 + 8 + 8 * 64 + 2 + 4)
+    # 11 scalars + 8 + 8*64 int32, then cond_upsample, n_upsample, upsample_strides[4], the three normaliser switches
+    assert ctypes.sizeof(L.PwvHparams) == 4 * (11 + 8 + 8 * 64 + 2 + 4 + 3)
 
 
 def _create(hp, precision='fp32'):

@@ -109,8 +109,10 @@ def test_stress_gain(hp, precision):
     noise, mel = O.synthetic_inputs(2, 2400, 80, 80)
     ref = _oracle(hp, weights, noise, mel)
     out, _ = _run(hp, weights, noise, mel)
+    # x3 kernels make the stack expansive: |wav| reaches ~120 and rounding noise is amplified the same way -- the EXACT fp32
+    # kernels sit at 0.64e-4 of max|ref| here, f16x3 at 0.69e-4 (profiles/r2_stress_diagnosis.txt); bound: 2e-4 of max|ref|
     scale = max(1.0, np.abs(ref).max())
-    assert np.abs(out.cpu().numpy() - ref).max() <= TOL * scale
+    assert np.abs(out.cpu().numpy() - ref).max() <= 2 * TOL * scale
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
@@ -127,8 +129,8 @@ def test_edge_shapes(hp, n, t, precision):
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'f16x3'])
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz'])
+@pytest.mark.parametrize('name,precision', [(n, p) for n in ('ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz')
+                                            for p in ('fp32', 'f16x3')] + [('ref_norm.npz', 'fp32'), ('ref_norm_tran.npz', 'fp32')])
 def test_golden_fixture(hp, name, precision):
     """Committed fixtures produced by executing the reference's own modules.py/models.py under the
     numpy TF stand-in (tests/golden/make_golden_from_reference.py): pinned to the reference's graph code, not to
@@ -262,6 +264,41 @@ def test_wide_channels_on_tensor_cores(hp, channels):
     errb = np.abs(outb.cpu().numpy() - ref).max()
     print(channels, 'channels bf16 max|delta| =', errb)
     assert np.isfinite(errb) and errb <= 6e-2 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize('which', ['all', 'flow', 'cond', 'wavenet', 'all+skip', 'all+tran', 'all+128'])
+def test_instance_normalisers(hp, which):
+    """model.normalize / normalize_cond / normalize_wavenet = 'in' (reference modules.py:274-284 at the call sites
+    models.py:27-29,70,121-122 and modules.py:149-257), each alone and all together, with use_skip_connection (every
+    layer's NORMALISED skip output is summed), with the transposed-conv conditioning (the reference's 4-D quirk) and at
+    128 channels: un-fused fp32 kernels against the oracle, random gamma / beta; layer and flow taps; bit-exact batch
+    independence (the statistics are per utterance)."""
+    channels = 128 if which == 'all+128' else 64
+    small_case(hp, channels=channels, dilations=((1, 2, 4, 512), (1, 8)), n=3, t=800, precision='fp32')
+    on = which.split('+')[0]
+    if on in ('all', 'flow'):
+        hp.model.normalize = 'in'
+    if on in ('all', 'cond'):
+        hp.model.normalize_cond = 'in'
+    if on in ('all', 'wavenet'):
+        hp.model.normalize_wavenet = 'in'
+    hp.model.use_skip_connection = which == 'all+skip'
+    if which == 'all+tran':
+        hp.model.cond_upsample_method = 'transposed_conv'
+    weights = pkg('weights').init_weights(hp, seed=19, bias_std=0.2)
+    noise, mel = O.synthetic_inputs(3, 800, 80, 80, mel_seed=3, noise_seed=4)
+    taps = {}
+    ref = _oracle(hp, weights, noise, mel, taps)
+    (out, cap), model = _run(hp, weights, noise, mel, taps={'flow_out': True, 'layer': (0, 1, 2)})
+    assert model.precision == 'fp32'
+    assert np.abs(cap['layer_out'].cpu().numpy() - taps['iaf_vocoder/iaf0/shifter/dilated_stack/layer2']).max() <= TOL
+    for i in range(2):
+        assert np.abs(cap['flow_out'][i].cpu().numpy() - taps[f'iaf_vocoder/iaf{i}']).max() <= TOL, i
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(which, 'max|delta| =', err)
+    assert err <= TOL
+    solo = model.forward(torch.from_numpy(noise[1:2]).cuda(), torch.from_numpy(mel[1:2]).cuda())
+    assert torch.equal(solo[0], out[1])
 
 
 @pytest.mark.parametrize('channels', [64, 128])

@@ -75,10 +75,10 @@ def test_length_must_be_multiple_of_hop(hp):
         O.iaf_vocoder_forward(noise, mel, weights, hp.model.dilations, 80)
 
 
-def test_instance_norm_variables_and_rejection_on_the_product_path(hp):
+def test_instance_norm_variables_on_the_product_path(hp):
     """With every normaliser set to 'in' the weight container lists the reference's beta/gamma variables at each call
     site (order pinned by the fixture generator against the reference's own graph code), the oracle normalises per
-    utterance and channel over time -- and the B200 path refuses the option instead of ignoring it."""
+    utterance and channel over time, and the C-ABI declares the same variable list ('bn' is refused, not ignored)."""
     small_case(hp, dilations=((1, 2), (4,)), n=2, t=160, precision='fp32')
     hp.model.normalize = hp.model.normalize_cond = hp.model.normalize_wavenet = 'in'
     W = pkg('weights')
@@ -92,8 +92,26 @@ def test_instance_norm_variables_and_rejection_on_the_product_path(hp):
     # the last flow's output went through normalize1: per utterance mean = beta, std = |gamma| (up to the 1e-8 epsilon)
     beta, gamma = float(weights['iaf_vocoder/normalize1/beta'][0]), float(weights['iaf_vocoder/normalize1/gamma'][0])
     assert np.allclose(out.mean(axis=1), beta, atol=1e-9) and np.allclose(out.std(axis=1), abs(gamma), rtol=1e-6)
+    pkg('vocoder')._assert_supported(hp)              # 'in' is on the B200 path (un-fused fp32 kernels, csrc/pwv_norm.cuh) ...
+    assert pkg('vocoder').resolve_precision(W.model_dims(hp), 'fp32') == 'fp32'
+    # ... and the C-ABI lists the same variables in the same order
+    import ctypes
+    L = pkg('_lib')
+    lib = L.load()
+    h = ctypes.c_void_p()
+    hparams = L.make_hparams(W.model_dims(hp), 'fp32')
+    assert lib.pwv_model_create(ctypes.byref(hparams), ctypes.byref(h)) == 0
+    name, shape, ndim = ctypes.c_char_p(), (ctypes.c_int64 * 4)(), ctypes.c_int()
+    got = []
+    for i in range(lib.pwv_model_num_variables(h)):
+        lib.pwv_model_variable(h, i, ctypes.byref(name), shape, ctypes.byref(ndim))
+        got.append(name.value.decode())
+    assert got == names
+    lib.pwv_model_destroy(h)
+    hparams = L.make_hparams(W.model_dims(hp), 'f16x3')           # a statistic over the whole time axis: fp32 kernels only
+    assert lib.pwv_model_create(ctypes.byref(hparams), ctypes.byref(h)) == -1 and b'normalisers' in lib.pwv_last_error()
+    hp.model.normalize = 'bn'                         # 'bn' (tf.layers.batch_normalization) stays unimplemented
     with pytest.raises(NotImplementedError):
         pkg('vocoder')._assert_supported(hp)
-    with pytest.raises(NotImplementedError):          # 'bn' has no variable layout here
-        hp.model.normalize = 'bn'
+    with pytest.raises(NotImplementedError):
         W.variable_shapes(hp)
