@@ -26,8 +26,15 @@
  * for the last failure on the calling thread. Buffers are contiguous row-major float32:
  * noise/wav [N][T], mel [N][1+T/hop][n_mels]. The library owns only the packed weights; the caller
  * owns inputs, outputs and workspace. pwv_forward enqueues on `stream` and returns without
- * synchronising; it allocates nothing. One model may be used from several host threads as long as
- * each uses its own workspace and stream. There is NO CPU fallback: without a CUDA device every
+ * synchronising; it allocates nothing. Threading: ONE forward in flight per model -- pwv_forward records its launch
+ * count and profiling events in the model and the kernels of consecutive layers hand tiles to each other through
+ * per-tile flags in the caller's workspace; use one model (the packed weights are 20 MB) and one workspace per host
+ * thread / stream. Several models may run concurrently on one device: every wait inside the kernels targets a kernel
+ * launched earlier on the same stream, never a CTA of the same grid, so no co-residency is assumed (the round-1
+ * whole-flow kernel, which did assume it, is reachable only through pwv_debug_set("path", 0)).
+ * Range: the tensor-core precisions hold activations as fp16 hi + lo (bf16 in PWV_PREC_BF16): |activation| > 65504
+ * overflows where the reference's fp32 would not -- not reachable with trained or Glorot-initialised weights, but a
+ * caller with exotic checkpoints should use PWV_PREC_FP32. There is NO CPU fallback: without a CUDA device every
  * compute entry point fails with PWV_ECUDA.
  */
 #ifndef PWV_H_

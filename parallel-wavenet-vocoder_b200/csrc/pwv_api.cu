@@ -261,6 +261,8 @@ static int configure_kernels(const pwv_model* m) {
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
+    PWV_CUDA(cudaFuncSetAttribute(pwv::k_layer_h<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TH_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<false, pwv::TW_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<false, pwv::TW_EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
     PWV_CUDA(cudaFuncSetAttribute(pwv::k_wide_h<true, pwv::TW_EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pwv::TW_SMEM_BYTES));
@@ -703,6 +705,12 @@ int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes) {
   Workspace w;
   carve(m, N, T, nullptr, &w);
   *bytes = w.bytes;
+  // A full-rate conditioning (cond_upsample_method 'transposed_conv', or normalize_cond) materialises the per-layer
+  // conditioning terms for every SAMPLE: [2][L][N][T][2C] floats. Say so instead of letting the caller's allocator fail.
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && w.bytes > total_b)
+    return fail(PWV_ENOMEM, "workspace for N=%d, T=%d is %zu bytes, the device has %zu%s", N, T, w.bytes, total_b,
+                cond_full_rate(m) ? " (full-rate conditioning: 2 x layers x N x T x 2C floats of per-layer conditioning terms; split the batch)" : "");
   return PWV_OK;
 }
 
@@ -1082,8 +1090,9 @@ static int encode_plane_map(CUtensorMap* map, void* base, int N, int T, int plan
 }
 
 template <bool BF16, bool LAST>
-static cudaError_t launch_layer_h(const cudaLaunchConfig_t* cfg, bool pk, const CUtensorMap& in, const CUtensorMap& out, const pwv::ThLayerParams& p) {
-  if (pk) return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, true>, in, out, p);
+static cudaError_t launch_layer_h(const cudaLaunchConfig_t* cfg, int variant, const CUtensorMap& in, const CUtensorMap& out, const pwv::ThLayerParams& p) {
+  if (variant == 2 && BF16) return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, true, false>, in, out, p);   // A/B: ex2 / rcp gate in bf16 mode
+  if (variant != 0) return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, true>, in, out, p);
   return cudaLaunchKernelEx(cfg, pwv::k_layer_h<BF16, LAST, false>, in, out, p);
 }
 
@@ -1150,7 +1159,7 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = (m->profiling == 1 || !m->use_pdl) ? 0 : 1;
-      const bool pk = m->tc_variant != 0;
+      const int pk = m->tc_variant;
       const CUtensorMap& in = maps_h[cur];
       const CUtensorMap& out = last ? maps_f[cur ^ 1] : maps_h[cur ^ 1];
       cudaError_t e;

@@ -365,7 +365,7 @@ __device__ __forceinline__ void split8x(const float (&v)[8], uint32_t* hi, uint3
 // Gate of 16 channels: z = tanh(f) * sigmoid(g) from the raw accumulators fr / gr, the epilogue scales
 // sf / sg and the pre-scaled conditioning rows cbf[0..3] / cbg[0..3] (float4 each). See the comments in
 // k_layer_tc's epilogue 1 for the arithmetic; PK = packed fp32x2 version of the same operations.
-template <bool BF16, bool PK, int NCH>
+template <bool BF16, bool PK, int NCH, bool TANH = BF16>
 __device__ __forceinline__ void tc_gate(const uint32_t (&fr)[NCH], const uint32_t (&gr)[NCH], const float4* cbf, const float4* cbg,
                                         float sf, float sg, float (&z)[NCH]) {
 #pragma unroll
@@ -373,7 +373,7 @@ __device__ __forceinline__ void tc_gate(const uint32_t (&fr)[NCH], const uint32_
     const float4 ca = cbf[q], cb4 = cbg[q];
     const float cf[4] = {ca.x, ca.y, ca.z, ca.w}, cg[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
     if (!PK) {
-      if (BF16) {
+      if (TANH) {
         // bf16 mode has no 1e-4 bar (operands carry 2^-9 relative error): one MUFU per transcendental,
         // tanh(f) * (0.5 + 0.5 tanh(g/2)). cbias/scales hold fe = -2 log2e f, ge = -log2e g.
 #pragma unroll
@@ -407,7 +407,7 @@ __device__ __forceinline__ void tc_gate(const uint32_t (&fr)[NCH], const uint32_
       for (int e = 0; e < 4; e += 2) {
         const uint64_t FE = fma2(pk2(__uint_as_float(fr[4 * q + e]), __uint_as_float(fr[4 * q + e + 1])), SF, pk2(cf[e], cf[e + 1]));
         const uint64_t GE = fma2(pk2(__uint_as_float(gr[4 * q + e]), __uint_as_float(gr[4 * q + e + 1])), SG, pk2(cg[e], cg[e + 1]));
-        if (BF16) {
+        if (TANH) {
           const uint64_t K = pk2(-0.34657359f, -0.34657359f), HALF = pk2(0.5f, 0.5f);
           float f0, f1, g0, g1;
           upk2(mul2(FE, K), f0, f1);

@@ -94,7 +94,8 @@ __device__ __forceinline__ void th_st_row64(uint8_t* box, int r, int c0, const u
     *reinterpret_cast<uint4*>(row + ((((c0 + c) ^ r) & 7) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
-template <bool BF16, bool LAST, bool PK = false>
+// TANH: the gate uses tanh.approx (one MUFU per transcendental, 2^-11 accuracy: bf16 mode) instead of the ex2 / rcp form
+template <bool BF16, bool LAST, bool PK = false, bool TANH = BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, ThLayerParams p) {
   using namespace ptx;
@@ -425,8 +426,8 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float z[16];
-          if (c == 0) tc_gate<BF16, PK, 16>(f0r, g0r, cb, cb + 16, sf, sg, z);
-          else tc_gate<BF16, PK, 16>(f1r, g1r, cb + 4, cb + 20, sf, sg, z);
+          if (c == 0) tc_gate<BF16, PK, 16, TANH>(f0r, g0r, cb, cb + 16, sf, sg, z);
+          else tc_gate<BF16, PK, 16, TANH>(f1r, g1r, cb + 4, cb + 20, sf, sg, z);
           if constexpr (LAST) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) zz[c * 16 + e] = z[e];

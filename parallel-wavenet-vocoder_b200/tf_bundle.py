@@ -204,18 +204,22 @@ def latest_checkpoint(logdir):
 
 
 def load_variables(prefix, names, use_ema=False, dtype=np.float32):
-    """name -> array for the requested variable names. With `use_ema`, `<name>/ExponentialMovingAverage`
-    is read when present -- the map reference generate.py:58-63 hands to tf.train.Saver."""
+    """name -> array for the requested variable names. With `use_ema` every variable is read from its
+    `<name>/ExponentialMovingAverage` shadow -- the map reference generate.py:58-63 hands to tf.train.Saver, whose
+    restore FAILS when a shadow is absent; so does this (a checkpoint without shadows would otherwise yield non-EMA
+    audio without any notice)."""
     reader = BundleReader(prefix)
+    suffix = '/ExponentialMovingAverage'
     out, missing = {}, []
     for name in names:
-        key = name + '/ExponentialMovingAverage' if use_ema and (name + '/ExponentialMovingAverage') in reader.entries else name
+        key = name + suffix if use_ema else name
         if key not in reader.entries:
-            missing.append(name)
+            missing.append(key)
             continue
         out[name] = reader.tensor(key).astype(dtype, copy=False)
     if missing:
-        raise KeyError('%d variables missing from %s, first: %s' % (len(missing), prefix, missing[0]))
+        hint = ' (train.use_ema is set but the checkpoint has no EMA shadows)' if use_ema and all(m.endswith(suffix) for m in missing) else ''
+        raise KeyError('%d variables missing from %s%s, first: %s' % (len(missing), prefix, hint, missing[0]))
     return out
 
 

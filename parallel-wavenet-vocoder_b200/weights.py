@@ -139,9 +139,11 @@ def load_npz(path, use_ema=False):
             continue
         out[name] = value
     if use_ema:
-        for name, value in raw.items():
-            if name.endswith(EMA_SUFFIX):
-                out[name[:-len(EMA_SUFFIX)]] = value
+        shadows = [name for name in raw if name.endswith(EMA_SUFFIX)]
+        if out and not shadows:
+            raise KeyError(f'{path}: train.use_ema is set but the container has no {EMA_SUFFIX} entries')
+        for name in shadows:
+            out[name[:-len(EMA_SUFFIX)]] = raw[name]
     return out
 
 

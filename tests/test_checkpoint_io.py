@@ -87,3 +87,21 @@ def test_io_finds_and_loads_checkpoints(hp, tmp_path):
     assert np.array_equal(got['iaf_vocoder/cond/dense'], live['iaf_vocoder/cond/dense'])
     with pytest.raises(FileNotFoundError):
         io.find_checkpoint(logdir, 'model-6')
+
+
+def test_use_ema_without_shadows_is_an_error(hp, tmp_path):
+    """tf.train.Saver(var_list={average_name: v}).restore fails on a checkpoint without shadows (reference
+    generate.py:58-63); falling back to the live variables silently would produce non-EMA audio."""
+    small_case(hp)
+    B = pkg('tf_bundle')
+    W = pkg('weights')
+    live, _, _ = _weights_with_ema(hp)
+    prefix = str(tmp_path / 'model-5')
+    B.write_bundle(prefix, live)
+    names = list(W.variable_shapes(hp).keys())
+    with pytest.raises(KeyError, match='no EMA shadows'):
+        B.load_variables(prefix, names, use_ema=True)
+    assert all(np.array_equal(B.load_variables(prefix, names)[k], live[k]) for k in names)
+    W.save_npz(str(tmp_path / 'w.npz'), live)
+    with pytest.raises(KeyError):
+        W.load_npz(str(tmp_path / 'w.npz'), use_ema=True)

@@ -292,11 +292,14 @@ def test_instance_normalisers(hp, which):
     (out, cap), model = _run(hp, weights, noise, mel, taps={'flow_out': True, 'layer': (0, 1, 2)})
     assert model.precision == 'fp32'
     assert np.abs(cap['layer_out'].cpu().numpy() - taps['iaf_vocoder/iaf0/shifter/dilated_stack/layer2']).max() <= TOL
+    # without the flow normaliser the waveform reaches |x| ~ 20 (unit-variance pre-activations into a x20 post-net): the
+    # bound scales with max|ref| there, as in the gain stress test
     for i in range(2):
-        assert np.abs(cap['flow_out'][i].cpu().numpy() - taps[f'iaf_vocoder/iaf{i}']).max() <= TOL, i
+        want = taps[f'iaf_vocoder/iaf{i}']
+        assert np.abs(cap['flow_out'][i].cpu().numpy() - want).max() <= TOL * max(1.0, float(np.abs(want).max())), i
     err = np.abs(out.cpu().numpy() - ref).max()
-    print(which, 'max|delta| =', err)
-    assert err <= TOL
+    print(which, 'max|delta| =', err, 'max|ref| =', np.abs(ref).max())
+    assert err <= TOL * max(1.0, float(np.abs(ref).max()))
     solo = model.forward(torch.from_numpy(noise[1:2]).cuda(), torch.from_numpy(mel[1:2]).cuda())
     assert torch.equal(solo[0], out[1])
 
