@@ -416,16 +416,18 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       float zz[LAST ? 32 : 1];                      // LAST: z kept until it is staged
       uint32_t dr[LAST ? 1 : 32], xh[LAST ? 1 : 16], xl[LAST ? 1 : 16];   // otherwise: D2 and the x[t] operand columns
       {
-        // both 16-channel chunks' accumulators are requested at once (one TMEM round trip; 64 registers)
+        // the second 16-channel chunk's accumulators are requested before the first chunk is computed: its TMEM round
+        // trip hides behind the first chunk's arithmetic (64 registers in flight)
         uint32_t f0r[16], g0r[16], f1r[16], g1r[16];
         tmem_ld16(tD + half * 32, f0r);
         tmem_ld16(tD + 64 + half * 32, g0r);
+        tmem_wait_ld();
         tmem_ld16(tD + half * 32 + 16, f1r);
         tmem_ld16(tD + 64 + half * 32 + 16, g1r);
-        tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float z[16];
+          if (c == 1) tmem_wait_ld();
           if (c == 0) tc_gate<BF16, PK, 16, TANH>(f0r, g0r, cb, cb + 16, sf, sg, z);
           else tc_gate<BF16, PK, 16, TANH>(f1r, g1r, cb + 4, cb + 20, sf, sg, z);
           if constexpr (LAST) {
@@ -474,7 +476,10 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         if (j >= 1) mbar_wait(&bars->y_full[slot], (j + 1) & 1);   // the store of tile j-1 has read the staging boxes
       }
       if (tracer) TC_TRACE(slot, j, 10);
-      named_bar_sync(1 + slot, 256);    // every thread of the slot is done reading the Y boxes: they become the staging
+      // The Y boxes become the staging of this tile's output. A thread's staging bytes (row r, chunks 4 half .. 4 half + 3
+      // of each plane) are exactly the bytes it read itself in a_copy, so no barrier is needed -- except in the flow's last
+      // layer, whose fp32 rows are twice as wide and overlap the other half's reads.
+      if constexpr (LAST) named_bar_sync(1 + slot, 256);
       // ---- residual + split (mode 0) / z (mode 1) -> staging boxes
       if constexpr (LAST) {
         uint8_t* row = stage + (2 + half) * TH_BOX_BYTES + r * 128;
