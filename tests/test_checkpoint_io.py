@@ -105,3 +105,25 @@ def test_use_ema_without_shadows_is_an_error(hp, tmp_path):
     W.save_npz(str(tmp_path / 'w.npz'), live)
     with pytest.raises(KeyError):
         W.load_npz(str(tmp_path / 'w.npz'), use_ema=True)
+
+
+def test_bundle_from_an_independent_encoder(hp):
+    """tests/golden/tf_fixture: a bundle written by a second encoder built from the format descriptions (no prefix
+    compression in the first block, several data blocks, a non-empty metaindex block, protobuf fields the reader must skip,
+    float64 / int32 / int64 entries) -- read back tensor for tensor, checksums verified, EMA map applied."""
+    import os
+    from conftest import ROOT
+    B = pkg('tf_bundle')
+    fx = os.path.join(ROOT, 'tests', 'golden', 'tf_fixture')
+    want = {k.replace('|', '/'): v for k, v in np.load(os.path.join(fx, 'expected.npz')).items()}
+    assert B.latest_checkpoint(fx) == os.path.join(fx, 'model-7')
+    r = B.BundleReader(os.path.join(fx, 'model-7'))
+    assert sorted(r.keys()) == sorted(want)
+    for name, arr in want.items():
+        got = r.tensor(name, verify=True)
+        assert got.dtype == arr.dtype and got.shape == arr.shape and np.array_equal(got, arr), name
+    names = ['iaf_vocoder/cond/dense', 'iaf_vocoder/iaf0/scalar/causal_layer/filter']
+    ema = B.load_variables(os.path.join(fx, 'model-7'), names, use_ema=True)
+    assert all(np.array_equal(ema[n], want[n + '/ExponentialMovingAverage']) for n in names)
+    live = B.load_variables(os.path.join(fx, 'model-7'), names)
+    assert all(np.array_equal(live[n], want[n]) for n in names)
