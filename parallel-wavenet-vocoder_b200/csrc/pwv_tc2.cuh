@@ -117,13 +117,16 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       for (int s = 0; s < 2; ++s) {
         mbar_init(&bars->x_full[s], 1);
         mbar_init(&bars->y_full[s], 1);
-        mbar_init(&bars->ax_ready[s], 256);
-        mbar_init(&bars->ay_ready[s], 256);
+        // (worker hand-offs: ONE arrival per warp -- lane 0, after the warp's lanes have fenced and met at __syncwarp.
+        //  256 per-thread arrivals on one mbarrier serialise in the shared-memory atomic unit, ~32 cycles per warp, and
+        //  that sat on the critical path of every hand-off: profiles/r2_trace_layer_h_v4*.txt)
+        mbar_init(&bars->ax_ready[s], 8);
+        mbar_init(&bars->ay_ready[s], 8);
         mbar_init(&bars->d1_ready[s], 1);
-        mbar_init(&bars->za_ready[s], 256);
-        mbar_init(&bars->zb_ready[s], 256);
+        mbar_init(&bars->za_ready[s], 8);
+        mbar_init(&bars->zb_ready[s], 8);
         mbar_init(&bars->d2_ready[s], 1);
-        mbar_init(&bars->out_ready[s], 256);
+        mbar_init(&bars->out_ready[s], 8);
       }
       bars->mma_lock = 0;
       fence_mbar_init();
@@ -361,6 +364,10 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
     const bool tracer = (warp & 7) == 0 && lane == 0;
     const int n_s = (n_local + 1 - slot) / 2;
 
+    auto warp_arrive = [&](uint64_t* bar) {     // every lane has fenced its own writes; the warp arrives once
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
     // boxes -> the slot's A columns, verbatim: K = channel (x[t-d]) / 64 + channel (x[t]), two 16-bit elements per column
     auto a_copy = [&](uint32_t par) {
       uint32_t v[16];
@@ -373,7 +380,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       if (p.split1) {                           // the x[t-d] half of K is handed over on its own: GEMM1 may start on it
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(&bars->ax_ready[slot]);
+        warp_arrive(&bars->ax_ready[slot]);
       }
       mbar_wait(&bars->y_full[slot], par);
 #pragma unroll
@@ -383,8 +390,11 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
       tmem_wait_st();
       tc_fence_before_sync();
-      if (!p.split1) mbar_arrive(&bars->ax_ready[slot]);
-      mbar_arrive(&bars->ay_ready[slot]);
+      __syncwarp();
+      if (lane == 0) {
+        if (!p.split1) mbar_arrive(&bars->ax_ready[slot]);
+        mbar_arrive(&bars->ay_ready[slot]);
+      }
     };
 
     if (n_s > 0) {
@@ -410,7 +420,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
 
       // ---- gate: z = tanh(f) * sigmoid(g) on my 32 channels
-      mbar_wait(&bars->d1_ready[slot], par);
+      mbar_wait_sleepy(&bars->d1_ready[slot], par);
       tc_fence_after_sync();
       if (tracer) TC_TRACE(slot, j, 5);
       float zz[LAST ? 32 : 1];                      // LAST: z kept until it is staged
@@ -445,8 +455,11 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
             if (c == 1 || p.split2) {          // (without the GEMM2 split both halves are handed over together)
               tmem_wait_st();
               tc_fence_before_sync();
-              if (c == 0 || !p.split2) mbar_arrive(&bars->za_ready[slot]);
-              if (c == 1) mbar_arrive(&bars->zb_ready[slot]);
+              __syncwarp();
+              if (lane == 0) {
+                if (c == 0 || !p.split2) mbar_arrive(&bars->za_ready[slot]);
+                if (c == 1) mbar_arrive(&bars->zb_ready[slot]);
+              }
             }
             if (p.z_out && t < p.T) {    // use_skip_connection (non-default): every layer's z feeds the skip sum (k_skip_simt)
               float4* zo = reinterpret_cast<float4*>(p.z_out + (((size_t)body * p.N + n) * p.T + t) * TC_C + half * 32 + c * 16);
@@ -459,7 +472,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       if constexpr (!LAST) {
         if (tracer) TC_TRACE(slot, j, 6);
         // ---- D2 and x[t] (hi, lo) of my 32 channels -> registers; after this the slot's TMEM belongs to the next tile
-        mbar_wait(&bars->d2_ready[slot], par);
+        mbar_wait_sleepy(&bars->d2_ready[slot], par);
         tc_fence_after_sync();
         if (tracer) TC_TRACE(slot, j, 7);
         tmem_ld32(tD + half * 32, dr);
@@ -514,7 +527,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         }
       }
       fence_proxy_async_smem();         // my staging writes -> visible to the TMA store the producer issues
-      mbar_arrive(&bars->out_ready[slot]);
+      warp_arrive(&bars->out_ready[slot]);
       if (tracer) TC_TRACE(slot, j, 8);
     }
   }
