@@ -309,8 +309,10 @@ def main():
         raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa_cpus = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        numa_cpus = pkg('dist').bind_to_gpu_numa(local_rank)   # the rank's host buffers and copy threads next to its GPU's PCIe root
         dist.init_process_group('nccl', device_id=dev)      # (NCCL's log lines go wherever NCCL_DEBUG sends them; fd 1 is guarded)
     if world != args.gpus and rank == 0:
         print(f'bench.py: note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}', file=sys.stderr)
@@ -475,11 +477,10 @@ def main():
         elif args.e2e_mode == 'hostshard':
             D = pkg('dist')
             batch = D.SharedHostBatch(n_job, t, t_mel, dims['n_mels'])
-            if rank == 0:
-                noise_all, mel_all = IO.synthetic_batch(n_job, t, dims['hop'], dims['n_mels'])
-                batch.fill(noise_all, mel_all)
-            else:
-                batch.fill(None, None)
+            noise_all, mel_all = IO.synthetic_batch(n_job, t, dims['hop'], dims['n_mels'])    # every rank: the same job batch ...
+            lo, hi = batch.bounds[rank]
+            batch.fill_shard(noise_all[lo:hi], mel_all[lo:hi])                                # ... of which it loads its own block
+            del noise_all, mel_all
             for _ in range(2):
                 D.hostshard_forward(model.forward_host, batch)
             e2e_s = 0.0
@@ -541,7 +542,8 @@ def main():
                       'bf16': 'bf16 (fp32 accumulate)'}[precision],
             'data': 'synthetic',
             'config': workload_config(args.workload, hp, world),
-            'engine': {'precision': precision, 'per_gpu_batch': n, 'activation_layout': 'planes' if planes_path else 'fp32 rows', 'debug': debug},
+            'engine': {'precision': precision, 'per_gpu_batch': n, 'activation_layout': 'planes' if planes_path else 'fp32 rows', 'debug': debug,
+                       'cpus_bound_to_gpu_socket': numa_cpus},
             'roofline': roofline, 'sustained': sustained, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
         }
         guard.emit(json.dumps(line))

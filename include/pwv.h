@@ -55,6 +55,7 @@ extern "C" {
 /* mel -> sample-rate conditioning (reference models.py:105-136) */
 #define PWV_UPSAMPLE_REPEAT 0            /* 1x1 conv + relu, every frame repeated hop times (default)       */
 #define PWV_UPSAMPLE_TRANSPOSED_CONV 1   /* stacked conv2d_transpose (kernel = stride) + relu per stage      */
+#define PWV_UPSAMPLE_NONE 2              /* any other method: no conditioning at all (models.py:134-135)   */
 #define PWV_NORM_NONE 0
 #define PWV_NORM_IN 1
 
@@ -90,7 +91,7 @@ typedef struct pwv_hparams {
   int32_t precision;              /* PWV_PREC_*                                                */
   int32_t n_layers[PWV_MAX_FLOWS];                     /* len(model.dilations[i])              */
   int32_t dilations[PWV_MAX_FLOWS][PWV_MAX_LAYERS];    /* model.dilations[i][j]                */
-  int32_t cond_upsample;          /* model.cond_upsample_method: PWV_UPSAMPLE_REPEAT | _TRANSPOSED_CONV  */
+  int32_t cond_upsample;          /* model.cond_upsample_method: PWV_UPSAMPLE_REPEAT | _TRANSPOSED_CONV | _NONE */
   int32_t n_upsample;             /* transposed_conv: number of stages (reference models.py:23: 3) ...   */
   int32_t upsample_strides[PWV_MAX_UPSAMPLE];  /* ... and their strides ([4,4,5]); product == hop_length  */
   /* normalisers (reference modules.py:263-284): PWV_NORM_NONE ('' / None) or PWV_NORM_IN ('in': instance normalisation

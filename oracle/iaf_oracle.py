@@ -288,10 +288,13 @@ def _forward(noise, mel, W, dilations, hop, use_biases, use_skip_connection, dty
     n, t, _ = x.shape
     if f'{ROOT}/cond/dense' in W:
         cond = upsample_cond_repeat(mel, W[f'{ROOT}/cond/dense'], hop)       # models.py:26,127-133
-    else:
+    elif f'{ROOT}/cond/transposed_conv_0_weights' in W:
         cond = upsample_cond_transposed(mel, W, UPSAMPLE_STRIDES, hop)       # models.py:26,109-124
-    cond = normalize(cond, W, f'{ROOT}/cond/normalize/normalize')            # models.py:27-29 (after the crop)
-    if cond.shape[1] != t:
+    else:
+        cond = None                                                          # models.py:134-135: any other method, no conditioning
+    if cond is not None:
+        cond = normalize(cond, W, f'{ROOT}/cond/normalize/normalize')        # models.py:27-29 (after the crop)
+    if cond is not None and cond.shape[1] != t:
         raise ValueError(f'cond length {cond.shape[1]} != {t}: length must be a multiple of hop '
                          f'and mel must have 1 + length//hop frames')
     for i, dil in enumerate(dilations):                                      # models.py:34

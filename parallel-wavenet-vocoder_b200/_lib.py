@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('PWV_LIB') or os.path.join(_HERE, 'libpwv_b200.so')   
 PWV_MAX_FLOWS = 8
 PWV_MAX_LAYERS = 64
 PWV_MAX_UPSAMPLE = 4
-UPSAMPLE = {'repeat': 0, 'transposed_conv': 1}
+UPSAMPLE = {'repeat': 0, 'transposed_conv': 1}      # any other method: 2 = no conditioning (reference models.py:134-135)
 PREC = {'fp32': 0, 'f16x3': 1, 'bf16': 2}
 
 EXPORTS = (
@@ -126,9 +126,7 @@ def make_hparams(dims, precision='fp32'):
     h.use_skip_connection = int(dims['use_skip'])
     h.precision = PREC[precision]
     method = dims.get('cond_upsample', 'repeat')
-    if method not in UPSAMPLE:
-        raise ValueError(f'model.cond_upsample_method must be one of {sorted(UPSAMPLE)}, got {method!r}')
-    h.cond_upsample = UPSAMPLE[method]
+    h.cond_upsample = UPSAMPLE.get(method, 2)
     strides = list(dims.get('upsample_strides', ())) if method == 'transposed_conv' else []
     if len(strides) > PWV_MAX_UPSAMPLE:
         raise ValueError(f'{len(strides)} upsample stages > {PWV_MAX_UPSAMPLE}')

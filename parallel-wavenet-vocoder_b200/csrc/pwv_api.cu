@@ -184,9 +184,10 @@ static void build_var_list(pwv_model* m) {
       norm("iaf_vocoder/cond/normalize_transposed_conv_" + std::to_string(i), Cc, nc);
       cin = Cc;
     }
-  } else {
+  } else if (hp.cond_upsample == PWV_UPSAMPLE_REPEAT) {
     add_var(m, "iaf_vocoder/cond/dense", {1, hp.n_mels, Cc});
   }
+  const bool conditioned = hp.cond_upsample != PWV_UPSAMPLE_NONE;     // reference models.py:134-135 / modules.py:216
   norm("iaf_vocoder/cond/normalize/normalize", Cc, nc);
   for (int i = 0; i < hp.n_iaf; ++i) {
     for (int b = 0; b < 2; ++b) {
@@ -197,8 +198,10 @@ static void build_var_list(pwv_model* m) {
         std::string q = p + "/dilated_stack/layer" + std::to_string(j);
         add_var(m, q + "/filter", {k, R, D});
         add_var(m, q + "/gate", {k, R, D});
-        add_var(m, q + "/gc_filter", {1, Cc, D});
-        add_var(m, q + "/gc_gate", {1, Cc, D});
+        if (conditioned) {
+          add_var(m, q + "/gc_filter", {1, Cc, D});
+          add_var(m, q + "/gc_gate", {1, Cc, D});
+        }
         if (hp.use_biases) {
           add_var(m, q + "/filter_bias", {D});
           add_var(m, q + "/gate_bias", {D});
@@ -305,8 +308,10 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (C != 64 && C != 128 && C != 256) return fail(PWV_EINVAL, "residual_channels=%d: supported 64, 128, 256", C);
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
-  if (hp->cond_upsample != PWV_UPSAMPLE_REPEAT && hp->cond_upsample != PWV_UPSAMPLE_TRANSPOSED_CONV)
+  if (hp->cond_upsample != PWV_UPSAMPLE_REPEAT && hp->cond_upsample != PWV_UPSAMPLE_TRANSPOSED_CONV && hp->cond_upsample != PWV_UPSAMPLE_NONE)
     return fail(PWV_EINVAL, "unknown cond_upsample %d", hp->cond_upsample);
+  if (hp->cond_upsample == PWV_UPSAMPLE_NONE && hp->normalize_cond)
+    return fail(PWV_EINVAL, "normalize_cond needs a conditioned graph (cond_upsample PWV_UPSAMPLE_NONE leaves none to normalise)");
   if (hp->cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV) {
     if (hp->n_upsample < 1 || hp->n_upsample > PWV_MAX_UPSAMPLE) return fail(PWV_EINVAL, "n_upsample=%d out of range [1,%d]", hp->n_upsample, PWV_MAX_UPSAMPLE);
     long long prod = 1;
@@ -416,10 +421,13 @@ int pwv_model_finalize(pwv_model* m) {
       cin = Cc;
     }
   } else {
-    m->off_wc = put((size_t)hp.n_mels * Cc);
-    const auto& w = var(m, "iaf_vocoder/cond/dense");
-    std::copy(w.begin(), w.end(), arena.begin() + m->off_wc);
+    m->off_wc = put((size_t)hp.n_mels * Cc);      // (zeros in an unconditional graph)
+    if (hp.cond_upsample == PWV_UPSAMPLE_REPEAT) {
+      const auto& w = var(m, "iaf_vocoder/cond/dense");
+      std::copy(w.begin(), w.end(), arena.begin() + m->off_wc);
+    }
   }
+  const bool conditioned = hp.cond_upsample != PWV_UPSAMPLE_NONE;
   m->off_colscale = put(2 * C);
   for (int c = 0; c < C; ++c) {
     arena[m->off_colscale + c] = pwv::TC_KF;
@@ -486,15 +494,19 @@ int pwv_model_finalize(pwv_model* m) {
               arena[lo.wfg + row * 2 * C + co] = wf[((size_t)tap * C + ci) * C + co];
               arena[lo.wfg + row * 2 * C + C + co] = wg[((size_t)tap * C + ci) * C + co];
             }
-        const auto& gf = var(m, q + "/gc_filter");   // [1][Cc][C]
-        const auto& gg = var(m, q + "/gc_gate");
+        // (unconditional graph: the conditioning projections stay zero, so the per-frame conditioning rows the
+        //  kernels add are just the filter / gate biases)
         const size_t wgc = m->off_wgc[i] + ((size_t)b * hp.n_layers[i] + j) * Cc * 2 * C;
         const size_t bfg = m->off_bfg[i] + ((size_t)b * hp.n_layers[i] + j) * 2 * C;
-        for (int c = 0; c < Cc; ++c)
-          for (int co = 0; co < C; ++co) {
-            arena[wgc + (size_t)c * 2 * C + co] = gf[(size_t)c * C + co];
-            arena[wgc + (size_t)c * 2 * C + C + co] = gg[(size_t)c * C + co];
-          }
+        if (conditioned) {
+          const auto& gf = var(m, q + "/gc_filter");   // [1][Cc][C]
+          const auto& gg = var(m, q + "/gc_gate");
+          for (int c = 0; c < Cc; ++c)
+            for (int co = 0; co < C; ++co) {
+              arena[wgc + (size_t)c * 2 * C + co] = gf[(size_t)c * C + co];
+              arena[wgc + (size_t)c * 2 * C + C + co] = gg[(size_t)c * C + co];
+            }
+        }
         lo.wd = put((size_t)C * C);
         lo.bd = put(C);
         lo.ws = put((size_t)C * S);
@@ -1115,11 +1127,11 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
   for (int i = 0; i < flow; ++i) layer_base += 2 * (size_t)hp.n_layers[i];
   int cur = *cur_buf;
   // Tile flags between consecutive layers let a layer's tiles start while the previous layer's tail is still running;
-  // they pay while a CTA owns few tiles per layer (round-1 sweep: 2.5 .. 17), beyond that the whole-kernel wait of the
+  // they pay while a CTA owns a handful of tiles per layer (round-1 sweep: 2.5 .. 17; below that a tile-level flag round trip per layer costs more than the whole-kernel wait: c1), beyond that the whole-kernel wait of the
   // programmatic dependent launch costs less than the flag traffic.
   const double tiles_per_cta = (double)tiles_body / (grid / 2);
   // (use_skip_connection puts a skip-sum kernel between consecutive layers: no tile handshake across it)
-  const bool layer_flags = m->use_flags && m->use_pdl && m->profiling != 1 && !hp.use_skip_connection && tiles_per_cta >= 1.5 && tiles_per_cta <= 17.0;
+  const bool layer_flags = m->use_flags && m->use_pdl && m->profiling != 1 && !hp.use_skip_connection && tiles_per_cta >= 2.5 && tiles_per_cta <= 17.0;
   const size_t plane_elems = (size_t)2 * N * T * C;
   using SCfg = pwv::TileCfg<64>;
   const dim3 sgrid((T + SCfg::TM - 1) / SCfg::TM, N, 2);
@@ -1367,6 +1379,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
                                cudaMemcpyDeviceToDevice, st));
   } else {
     // conditioning: cproj = relu(mel . Wc)   (reference models.py:128-130, at mel rate)
+    if (hp.cond_upsample == PWV_UPSAMPLE_NONE) {              // reference models.py:134-135: no conditioning; `mel` is not read
+      PWV_CUDA(cudaMemsetAsync(w.cproj, 0, sizeof(float) * (size_t)N * t_mel * Cc, st));
+    } else {
     const bool full = hp.normalize_cond == PWV_NORM_IN;       // then the repeated, cropped rows are materialised for the statistics
     pwv::RowGemmBatch rb{m->d_arena + m->off_wc, 0, nullptr, 0, full ? w.up[0] : w.cproj, 0, nullptr};
     const int M = N * t_mel;
@@ -1377,6 +1392,7 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       const size_t n_el = (size_t)N * T * Cc;
       pwv::k_repeat_crop<<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(w.up[0], w.cproj, N, T, t_mel, hp.hop_length, Cc);
       ++launches;
+    }
     }
   }
   if (hp.normalize_cond == PWV_NORM_IN) {                       // models.py:27-29, after the crop

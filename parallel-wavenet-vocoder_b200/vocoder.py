@@ -26,10 +26,11 @@ def _assert_supported(hp):
         if m.get(key) and m[key] != 'in':
             raise NotImplementedError(f"model.{key}={m[key]!r}: '' and 'in' (instance normalisation over time, reference "
                                       f"modules.py:274-284) are on the B200 path; 'bn' (tf.layers.batch_normalization) is not")
-    if m.cond_upsample_method not in ('repeat', 'transposed_conv'):
-        # the reference then conditions on nothing (models.py:134-135: cond = None)
-        raise NotImplementedError(f"model.cond_upsample_method={m.cond_upsample_method!r}: 'repeat' "
-                                  f"(reference models.py:127-133) and 'transposed_conv' (models.py:109-124) are on the B200 path")
+    # cond_upsample_method outside 'repeat' / 'transposed_conv': the reference conditions on nothing (models.py:134-135:
+    # cond = None, no cond/* and gc_* variables) -- so does this path; normalize_cond would then normalise None there
+    if m.cond_upsample_method not in ('repeat', 'transposed_conv') and m.get('normalize_cond'):
+        raise ValueError(f"model.cond_upsample_method={m.cond_upsample_method!r} leaves the graph unconditional; "
+                         f"normalize_cond={m['normalize_cond']!r} cannot apply (the reference fails there too, models.py:27-29)")
     strides = list(W.UPSAMPLE_STRIDES)   # the reference asserts this even for 'repeat' (models.py:26,106)
     if int(np.prod(strides)) != int(hp.signal.hop_length):
         raise AssertionError(f'prod({strides}) != hop_length {hp.signal.hop_length} (reference models.py:106)')

@@ -53,8 +53,11 @@ def variable_shapes(hp):
             shapes[f'{ROOT}/cond/transposed_conv_{i}_weights'] = (1, stride, Cc, cin)
             norm(f'{ROOT}/cond/normalize_transposed_conv_{i}', Cc, nc)       # models.py:121-122
             cin = Cc
-    else:
+    elif d['cond_upsample'] == 'repeat':
         shapes[f'{ROOT}/cond/dense'] = (1, d['n_mels'], Cc)
+    conditioned = d['cond_upsample'] in ('repeat', 'transposed_conv')        # anything else: cond = None (models.py:134-135)
+    if not conditioned and nc:
+        raise ValueError("normalize_cond with an unconditional graph: the reference fails too (normalize(None), models.py:27-29)")
     norm(f'{ROOT}/cond/normalize/normalize', Cc, nc)                         # models.py:27-29
     for i in range(d['n_iaf']):
         for body in BODIES:
@@ -65,8 +68,9 @@ def variable_shapes(hp):
                 q = f'{p}/dilated_stack/layer{j}'
                 shapes[f'{q}/filter'] = (k, R, D)
                 shapes[f'{q}/gate'] = (k, R, D)
-                shapes[f'{q}/gc_filter'] = (1, Cc, D)
-                shapes[f'{q}/gc_gate'] = (1, Cc, D)
+                if conditioned:                                              # modules.py:216-222: only with a condition
+                    shapes[f'{q}/gc_filter'] = (1, Cc, D)
+                    shapes[f'{q}/gc_gate'] = (1, Cc, D)
                 if d['use_biases']:
                     shapes[f'{q}/filter_bias'] = (D,)
                     shapes[f'{q}/gate_bias'] = (D,)

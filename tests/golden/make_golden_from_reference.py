@@ -166,6 +166,23 @@ def main():
         for key in norm:
             setattr(ref_hp.model, key, '')
     ref_hp.model.cond_upsample_method = 'repeat'
+
+    # ---- fixture 7: any other cond_upsample_method leaves the graph UNCONDITIONAL (reference models.py:134-135: cond = None,
+    #      so no cond/* variable and no gc_filter / gc_gate in any layer, modules.py:216-222)
+    ref_hp.model.cond_upsample_method = 'none'
+    my_hp.set_hparam_dict({'model': {'n_iaf': 2, 'dilations': dil, 'cond_upsample_method': 'none'}}, case='golden/nocond')
+    weights = W.init_weights(my_hp, seed=48, bias_std=0.1, dtype=np.float32)
+    wav, created = run_reference(tf, ref_models, weights, noise, mel)
+    assert created == list(W.variable_shapes(my_hp).keys()), 'variable list / creation order differs (unconditional)'
+    assert not any('/cond/' in v or '/gc_' in v for v in created)
+    ours = O.iaf_vocoder_forward(noise, mel, weights, dil, hop, dtype=np.float64)
+    err = np.abs(ours - wav).max()
+    print('unconditional graph: reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (err, np.abs(wav).max()))
+    assert err < 1e-12
+    d = pack(noise, mel, wav, weights, dil, (48, 0.1, 1.0))
+    d['cond_upsample_method'] = np.array('none')
+    np.savez_compressed(os.path.join(HERE, 'ref_nocond.npz'), **d)
+    ref_hp.model.cond_upsample_method = 'repeat'
     print('wrote ref_small.npz, ref_flows.npz, ref_varlist.txt (%d variables in the default graph)' % len(W.variable_shapes(my_hp.set_hparam_yaml('default'))))
 
 

@@ -143,3 +143,28 @@ def test_plain_c_consumer_builds_and_runs(tmp_path):
     out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert out.returncode == 0, out.stdout
     assert 'c_abi_smoke ok' in out.stdout
+
+
+def test_unconditional_graph_variable_list(hp):
+    """cond_upsample_method outside 'repeat' / 'transposed_conv' leaves the graph unconditional (reference
+    models.py:134-135, modules.py:216-222): no cond/* variable, no gc_filter / gc_gate -- in the weight container and
+    in the C-ABI's variable list alike; normalize_cond cannot apply."""
+    small_case(hp)
+    hp.model.cond_upsample_method = 'none'
+    W, L = pkg('weights'), pkg('_lib')
+    names = list(W.variable_shapes(hp).keys())
+    assert not any('/cond/' in n or '/gc_' in n for n in names)
+    lib, h, rc = _create(hp)
+    assert rc == 0
+    name, shape, ndim = ctypes.c_char_p(), (ctypes.c_int64 * 4)(), ctypes.c_int()
+    got = []
+    for i in range(lib.pwv_model_num_variables(h)):
+        lib.pwv_model_variable(h, i, ctypes.byref(name), shape, ctypes.byref(ndim))
+        got.append(name.value.decode())
+    assert got == names
+    lib.pwv_model_destroy(h)
+    hp.model.normalize_cond = 'in'
+    with pytest.raises(ValueError):
+        W.variable_shapes(hp)
+    with pytest.raises(ValueError):
+        pkg('vocoder')._assert_supported(hp)

@@ -81,8 +81,11 @@ def _worker_hostshard(rank, world, port, n_total, out_path):
     g = torch.Generator().manual_seed(11)
     noise = torch.randn((n_total, t), generator=g)
     mel = torch.randn((n_total, t_mel, n_mels), generator=g)
-    batch.fill(noise if rank == 0 else None, mel if rank == 0 else None)
     lo, hi = batch.bounds[rank]
+    if n_total % 2:                                      # both ways of loading the batch
+        batch.fill(noise if rank == 0 else None, mel if rank == 0 else None)
+    else:
+        batch.fill_shard(noise[lo:hi], mel[lo:hi])
     nz, ml, wv = batch.shard()
     assert nz.shape == (hi - lo, t) and ml.shape == (hi - lo, t_mel, n_mels) and wv.shape == (hi - lo, t)
     assert nz.is_contiguous() and ml.is_contiguous() and wv.is_contiguous()

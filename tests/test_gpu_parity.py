@@ -129,7 +129,7 @@ def test_edge_shapes(hp, n, t, precision):
     assert np.abs(out.cpu().numpy() - ref).max() <= TOL
 
 
-@pytest.mark.parametrize('name,precision', [(n, p) for n in ('ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz')
+@pytest.mark.parametrize('name,precision', [(n, p) for n in ('ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz', 'ref_nocond.npz')
                                             for p in ('fp32', 'f16x3')] + [('ref_norm.npz', 'fp32'), ('ref_norm_tran.npz', 'fp32')])
 def test_golden_fixture(hp, name, precision):
     """Committed fixtures produced by executing the reference's own modules.py/models.py under the

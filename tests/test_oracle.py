@@ -9,7 +9,7 @@ from conftest import ROOT, load_golden, pkg, small_case
 from oracle import iaf_oracle as O
 
 
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz', 'ref_norm.npz', 'ref_norm_tran.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz', 'ref_norm.npz', 'ref_norm_tran.npz', 'ref_nocond.npz'])
 def test_oracle_reproduces_reference_golden(hp, name):
     weights, noise, mel, wav, dil = load_golden(hp, name)
     skip = name == 'ref_skip.npz'        # generated with model.use_skip_connection=True
