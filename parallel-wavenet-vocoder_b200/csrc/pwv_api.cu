@@ -125,6 +125,7 @@ struct pwv_model {
   int tc_seg = 0;                // "seg" (path 0): k_flow_tc gated layers per launch (0 = by job size)
   int tc_variant = PWV_TC_VARIANT_DEFAULT;   // "variant": 0 scalar epilogue arithmetic, 1 packed fp32x2, 2 (path 0) setmaxnreg register re-partition
   bool trace_flow = false;       // "trace_flow" (path 0): the phase trace follows k_flow_tc instead of forcing per-layer launches
+  bool use_cp = false;           // "cp" (path 1): boxes -> TMEM by tcgen05.cp from the MMA issuer instead of the workers' ld.shared + tcgen05.st
   bool split1 = false;           // "split1" (path 1): GEMM1 starts on the x[t-d] half of K before the x[t] boxes are copied
   bool split2 = false;           // "split2" (path 1): GEMM2 starts on the first half of the z chunks
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
@@ -1155,6 +1156,7 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
       p.done_in = p.flags_in ? done - 1 : nullptr;
       p.done_target = 2 * grid;          // both producers of every CTA of the previous layer's grid (same grid for the whole flow)
     }
+    p.use_cp = m->use_cp ? 1 : 0;
     p.split1 = m->split1 ? 1 : 0;
     p.split2 = m->split2 ? 1 : 0;
     p.z_out = (hp.use_skip_connection && !last) ? w.zbuf : nullptr;
@@ -1608,6 +1610,7 @@ int pwv_debug_set(pwv_model* m, const char* key, int value) {
   else if (k == "seg") m->tc_seg = value;
   else if (k == "variant") { if (value < 0 || value > 2) return fail(PWV_EINVAL, "variant must be 0, 1 or 2"); m->tc_variant = value; }
   else if (k == "trace_flow") m->trace_flow = value != 0;
+  else if (k == "cp") m->use_cp = value != 0;
   else if (k == "split1") m->split1 = value != 0;
   else if (k == "split2") m->split2 = value != 0;
   else return fail(PWV_EINVAL, "unknown debug switch '%s'", key);

@@ -199,6 +199,24 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t smem_add
   return d;
 }
 
+// Shared-memory matrix descriptor, K-major, 128B swizzle (the layout a TMA box with CU_TENSOR_MAP_SWIZZLE_128B and
+// 128-byte rows lands in): SBO = 8 rows x 128 B = 1024, LBO unused (1), layout type 2. A K step of 16 sixteen-bit elements
+// advances the start address by 32 bytes inside the swizzle span. (Verified by tools/cp_probe.cu on B200.)
+__device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// shared memory -> tensor memory, 128 lanes x 256 bits (= 8 columns: one K step of a kind::f16 A operand), issued by one
+// thread, executed in order with that thread's tcgen05.mma; completion through tcgen05.commit
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
+
 // Instruction descriptor for kind::f16 (A/B fp16 or bf16, fp32 accumulate), both operands K-major.
 // Bits: [4,6) D format (1 = f32), [7,10) A format, [10,13) B format (0 = f16, 1 = bf16),
 // [15] A major, [16] B major (0 = K), [17,23) N>>3, [24,29) M>>4.

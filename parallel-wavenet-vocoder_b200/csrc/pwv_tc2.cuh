@@ -66,6 +66,7 @@ struct ThLayerParams {
   int done_target;
   // Measured and left off (profiles/r2_ab_layer_h.txt: no gain; with the MMA lock released between the halves the two
   // slots' GEMMs interleave and the slots fall into lock-step, the effect DESIGN 4.1 describes for round 1):
+  int use_cp;               // 1: the MMA issuer moves the landed boxes into TMEM itself (tcgen05.cp) instead of the workers
   int split1;               // 1: GEMM1 starts on the x[t-d] half of K as soon as those columns are copied (the x[t] boxes land later)
   int split2;               // 1: GEMM2 starts on the first 16-channel chunk of each half of z while the gate computes the second
   long long* trace;
@@ -74,6 +75,7 @@ struct ThLayerParams {
 struct ThBarriers {
   uint64_t w_ready;
   uint64_t x_full[2], y_full[2], ax_ready[2], ay_ready[2], d1_ready[2], za_ready[2], zb_ready[2], d2_ready[2], out_ready[2];
+  uint64_t a_free[2], boxes_free[2];      // use_cp: slot's TMEM free for the next tile (8 warp arrivals) / its boxes copied (commit)
   uint32_t tmem_base;
   int mma_lock;
 };
@@ -127,6 +129,8 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         mbar_init(&bars->zb_ready[s], 8);
         mbar_init(&bars->d2_ready[s], 1);
         mbar_init(&bars->out_ready[s], 8);
+        mbar_init(&bars->a_free[s], 8);
+        mbar_init(&bars->boxes_free[s], 1);
       }
       bars->mma_lock = 0;
       fence_mbar_init();
@@ -188,8 +192,30 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 #pragma unroll 1
         for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
       };
+      const uint32_t box0 = smem_u32(smem + TH_SMEM_STAGE0 + s * TH_STAGE_BYTES);
       for (int j = 0; j < tiles_s; ++j) {
         const uint32_t par = j & 1;
+        if (p.use_cp) {
+          // the landed boxes go into the slot's A columns by tcgen05.cp, in order with the MMAs that read them
+          if (j > 0) mbar_wait(&bars->a_free[s], (j - 1) & 1);      // the workers have read D2 and x of the slot's previous tile
+          mbar_wait(&bars->x_full[s], par);
+          mbar_wait(&bars->y_full[s], par);
+          tc_lock<SPLIT>(&bars->mma_lock);
+          tc_fence_after_sync();
+          TC_TRACE(2, j, s * 8 + 0);
+#pragma unroll 1
+          for (int b = 0; b < 2; ++b)            // b = 0: x[t-d] boxes -> K 0..63, b = 1: x[t] boxes -> K 64..127
+#pragma unroll 1
+            for (int q = 0; q < P; ++q)
+#pragma unroll 1
+              for (int k = 0; k < 4; ++k)
+                tmem_cp_128x256b((q ? tAlo : tAhi) + b * 32 + k * 8, smem_desc_kmajor_sw128(box0 + (2 * b + q) * TH_BOX_BYTES + k * 32));
+          mma_commit(&bars->boxes_free[s]);
+          gemm1_part(0, 8, 0);
+          mma_commit(&bars->d1_ready[s]);
+          tc_unlock<SPLIT>(&bars->mma_lock);
+          TC_TRACE(2, j, s * 8 + 1);
+        } else {
         mbar_wait(&bars->ax_ready[s], par);
         if (p.split1) {                    // the x[t-d] half of K (columns copied first) ...
           tc_lock<SPLIT>(&bars->mma_lock);
@@ -210,6 +236,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         mma_commit(&bars->d1_ready[s]);
         tc_unlock<SPLIT>(&bars->mma_lock);
         TC_TRACE(2, j, s * 8 + 1);
+        }
         if (LAST) continue;
         // z columns: step 0 / 1 = first / second 16-channel chunk of the workers' half 0, steps 2 / 3 of half 1
         mbar_wait(&bars->za_ready[s], par);
@@ -306,16 +333,18 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         issue_x(0);
         issue_y(0);
       }
+      uint64_t* const boxes_copied = p.use_cp ? bars->boxes_free : bars->ay_ready;     // tile's boxes are in TMEM
+      uint64_t* const xboxes_copied = p.use_cp ? bars->boxes_free : bars->ax_ready;
       if (tiles_s > 1) {                                // both landing areas are free once tile 0 sits in TMEM
         wait_tiles(1);
-        mbar_wait(&bars->ay_ready[s], 0);
+        mbar_wait(&boxes_copied[s], 0);
         issue_x(1);
         issue_y(1);
       }
       if (tiles_s > 2) wait_tiles(2);                   // the probes run one tile ahead, in the producer's idle time
       for (int j = 0; j < tiles_s; ++j) {
         if (j + 1 < tiles_s) {
-          mbar_wait(&bars->ax_ready[s], (j + 1) & 1);   // tile j+1's x[t-d] columns are in TMEM: the X boxes are free
+          mbar_wait(&xboxes_copied[s], (j + 1) & 1);    // tile j+1's x[t-d] columns are in TMEM: the X boxes are free
           if (j + 2 < tiles_s) {
             issue_x(j + 2);
             TC_TRACE(3, j, s * 8 + 0);
@@ -399,7 +428,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 
     if (n_s > 0) {
       if (tracer) TC_TRACE(slot, 0, 0);
-      a_copy(0);
+      if (!p.use_cp) a_copy(0);
       if (tracer) TC_TRACE(slot, 0, 4);
       mbar_wait(&bars->w_ready, 0);
     }
@@ -420,6 +449,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
 
       // ---- gate: z = tanh(f) * sigmoid(g) on my 32 channels
+      if (p.use_cp) mbar_wait(&bars->x_full[slot], par);      // (the conditioning rows ride on this barrier; long complete)
       mbar_wait_sleepy(&bars->d1_ready[slot], par);
       tc_fence_after_sync();
       if (tracer) TC_TRACE(slot, j, 5);
@@ -482,7 +512,12 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
       if (tracer) TC_TRACE(slot, j, 9);
       // ---- the slot's next tile goes into TMEM (its boxes landed long ago); GEMM1(j+1) starts when all 256 are through
-      if (j + 1 < n_s) {
+      if (p.use_cp) {
+        tc_fence_before_sync();
+        warp_arrive(&bars->a_free[slot]);            // my part of D2 / x is in registers: the slot's TMEM may take the next tile
+        if (j + 1 < n_s) mbar_wait(&bars->boxes_free[slot], (j + 1) & 1);   // ... whose boxes must have left before they become the staging
+        else if (j >= 1) mbar_wait(&bars->y_full[slot], (j + 1) & 1);
+      } else if (j + 1 < n_s) {
         a_copy((j + 1) & 1);
       } else {
         tc_fence_before_sync();

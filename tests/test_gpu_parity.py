@@ -385,6 +385,34 @@ def test_layer_kernel_variants_bit_identical(hp, path, variant, precision):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
+@pytest.mark.parametrize('switches', [{'cp': 1}, {'split1': 1, 'split2': 1}, {'tile_flags': 0}, {'pdl': 0}])
+def test_layer_h_switches_bit_identical(hp, precision, switches):
+    """k_layer_h's A/B switches change WHO moves operands and WHEN the MMAs are issued, never the arithmetic: boxes into
+    TMEM by tcgen05.cp from the MMA issuer ('cp'), K-split GEMMs, no tile flags, no programmatic dependent launch --
+    outputs bit-identical to the default on the default graph, ragged / d >= T shapes, one-tile slots and the c2 batch."""
+    W = pkg('weights')
+    cases = [(None, 2, 4000), (((1, 512, 2), (256, 1)), 5, 1040), (((1, 512, 2), (256, 1)), 1, 80), (((1,), (2, 4), (128,)), 3, 2000), (None, 8, 16000)]
+    for dil, n, t in cases:
+        if dil is None:
+            hp.set_hparam_yaml('default')
+            hp.engine.precision = precision
+        else:
+            small_case(hp, dilations=dil, n=n, t=t, precision=precision)
+        weights = W.init_weights(hp, seed=8, bias_std=0.1)
+        noise, mel = O.synthetic_inputs(n, t, 80, 80, mel_seed=51, noise_seed=52)
+        base, _ = _run(hp, weights, noise, mel, precision=precision)
+        got, model = _run(hp, weights, noise, mel, precision=precision, debug=switches)
+        again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
+        assert torch.equal(got, again), (dil, n, t, 'not deterministic')
+        if 'split1' in switches:          # a different order of the fp32 accumulations inside the tensor core
+            assert (got - base).abs().max() <= 1e-5 * max(1.0, float(base.abs().max())), (dil, n, t)
+        else:
+            assert torch.equal(got, base), (dil, n, t, float((got - base).abs().max()))
+        del model
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
 @pytest.mark.parametrize('quiet,rotate,seg', [(0, 0, 100), (0, 1, 100), (0, 1, 1), (0, 0, 3), (0, 0, 0)])
 def test_flow_kernel_bit_identical_to_layer_kernels(hp, precision, quiet, rotate, seg):
     """Round-1 kernels (debug path 0). k_flow_tc (one persistent launch per flow, tiles of consecutive layers chained by per-tile flags) runs
