@@ -449,7 +449,9 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
 
       // ---- gate: z = tanh(f) * sigmoid(g) on my 32 channels
-      if (p.use_cp) mbar_wait(&bars->x_full[slot], par);      // (the conditioning rows ride on this barrier; long complete)
+      // (use_cp: the conditioning rows rode on x_full, which the MMA issuer waited for before the GEMM whose completion is
+      //  awaited here -- the workers must NOT wait on x_full themselves: by now it may be two phases ahead and a parity
+      //  wait would alias, measured as a hang)
       mbar_wait_sleepy(&bars->d1_ready[slot], par);
       tc_fence_after_sync();
       if (tracer) TC_TRACE(slot, j, 5);
