@@ -405,7 +405,10 @@ def test_layer_h_switches_bit_identical(hp, precision, switches):
         again = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
         assert torch.equal(got, again), (dil, n, t, 'not deterministic')
         if 'split1' in switches:          # a different order of the fp32 accumulations inside the tensor core
-            assert (got - base).abs().max() <= 1e-5 * max(1.0, float(base.abs().max())), (dil, n, t)
+            # (bf16: a last-bit difference of an fp32 accumulator can flip the bf16 rounding of a stored activation, so
+            #  the two orders differ by bf16 steps, inside that precision's own bound)
+            tol = 1e-5 if precision == 'f16x3' else 6e-2
+            assert (got - base).abs().max() <= tol * max(1.0, float(base.abs().max())), (dil, n, t)
         else:
             assert torch.equal(got, base), (dil, n, t, float((got - base).abs().max()))
         del model
