@@ -104,6 +104,7 @@ struct pwv_model {
   std::vector<size_t> off_wgc, off_bfg;
   size_t off_colscale = 0;       // [2C]: -2log2e (filter half), -log2e (gate half) for the tensor-core epilogue
   int num_sms = 148;
+  size_t dev_total_bytes = 0;      // cudaMemGetInfo at finalize (a driver query: never on the per-call path)
 
   pwv::TcModel tc;               // tensor-core weight images (empty in fp32 mode)
   pwv::TwModel tw;               // weight streams of the wide tensor-core kernels (C > 64)
@@ -554,6 +555,10 @@ int pwv_model_finalize(pwv_model* m) {
   }
   PWV_CUDA(cudaGetDevice(&m->device));
   PWV_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) m->dev_total_bytes = total_b;
+  }
   if (m->d_arena) { cudaFree(m->d_arena); m->d_arena = nullptr; }
   m->arena_floats = arena.size();
   PWV_CUDA(cudaMalloc(&m->d_arena, arena.size() * sizeof(float)));
@@ -720,8 +725,10 @@ int pwv_workspace_bytes(const pwv_model* m, int N, int T, size_t* bytes) {
   *bytes = w.bytes;
   // A full-rate conditioning (cond_upsample_method 'transposed_conv', or normalize_cond) materialises the per-layer
   // conditioning terms for every SAMPLE: [2][L][N][T][2C] floats. Say so instead of letting the caller's allocator fail.
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && w.bytes > total_b)
+  // (the device's size was read once at finalize: with 8 ranks calling at the same moment a cudaMemGetInfo per call
+  //  measured as milliseconds per pwv_forward_host)
+  const size_t total_b = m->dev_total_bytes;
+  if (total_b && w.bytes > total_b)
     return fail(PWV_ENOMEM, "workspace for N=%d, T=%d is %zu bytes, the device has %zu%s", N, T, w.bytes, total_b,
                 cond_full_rate(m) ? " (full-rate conditioning: 2 x layers x N x T x 2C floats of per-layer conditioning terms; split the batch)" : "");
   return PWV_OK;

@@ -49,6 +49,45 @@ def main():
         dist.barrier()
         ts.append(time.perf_counter() - t0)
     out['barrier'] = sorted(ts)[len(ts) // 2] * 1e3
+    # the driver query pwv_forward_host made per call until this probe was written, all ranks at once
+    ts = []
+    for _ in range(10):
+        dist.barrier()
+        t0 = time.perf_counter()
+        torch.cuda.mem_get_info()
+        ts.append(time.perf_counter() - t0)
+    out['memgetinfo'] = sorted(ts)[len(ts) // 2] * 1e3
+    # the whole path on this rank's shard: pwv_forward_host from the shared batch / from private pinned buffers /
+    # pwv_forward on device-resident inputs, each step released by a barrier as in bench.py's e2e leg
+    hp = importlib.import_module('parallel-wavenet-vocoder_b200.hparam').hparam
+    W = importlib.import_module('parallel-wavenet-vocoder_b200.weights')
+    V = importlib.import_module('parallel-wavenet-vocoder_b200.vocoder')
+    hp.set_hparam_yaml('bench/c4')
+    dims = W.model_dims(hp)
+    model = V.PwvModel(dims, W.init_weights(hp, seed=0), 'f16x3')
+    d_nz.normal_()
+    d_ml.uniform_(-1, 1)
+    nz.copy_(d_nz)
+    ml.copy_(d_ml)
+    p_nz.copy_(d_nz)
+    p_ml.copy_(d_ml)
+    legs = (('fwd_host_shared', lambda: model.forward_host(nz, ml, wv)), ('fwd_host_private', lambda: model.forward_host(p_nz, p_ml, p_wv)),
+            ('fwd_device', lambda: (model.forward(d_nz, d_ml), torch.cuda.synchronize())))
+    for name, fn in legs:
+        for _ in range(2):
+            fn()
+        ts, tb = [], []
+        for _ in range(8):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            fn()
+            t1 = time.perf_counter()
+            dist.barrier()
+            ts.append(t1 - t0)
+            tb.append(time.perf_counter() - t0)
+        out[name] = sorted(ts)[len(ts) // 2] * 1e3
+        out[name + '+barrier'] = sorted(tb)[len(tb) // 2] * 1e3
     mb = (nz.numel() + ml.numel() + wv.numel()) * 4 / 1e6
     res = [None] * world
     dist.all_gather_object(res, (rank, out, cpus))
@@ -56,6 +95,9 @@ def main():
         for r, o, c in res:
             print('rank %d: %.1f MB per step; shared %.3f ms (%.1f GB/s)  private pinned %.3f ms (%.1f GB/s)  barrier %.3f ms  cpus bound %s'
                   % (r, mb, o['shared'], mb / o['shared'], o['private'], mb / o['private'], o['barrier'], c))
+            print('        cudaMemGetInfo %.3f ms | forward_host shared %.3f (+barrier %.3f)  private %.3f (+barrier %.3f)  forward on device %.3f (+barrier %.3f) ms'
+                  % (o['memgetinfo'], o['fwd_host_shared'], o['fwd_host_shared+barrier'], o['fwd_host_private'], o['fwd_host_private+barrier'],
+                     o['fwd_device'], o['fwd_device+barrier']))
     batch.close()
     dist.destroy_process_group()
 
