@@ -47,10 +47,11 @@
 extern "C" {
 #endif
 
-#define PWV_VERSION 200          /* major*10000 + minor*100 + patch */
+#define PWV_VERSION 201          /* major*10000 + minor*100 + patch */
 #define PWV_MAX_FLOWS 8
 #define PWV_MAX_LAYERS 64
 #define PWV_MAX_UPSAMPLE 4
+#define PWV_MAX_FILTER_WIDTH 32
 
 /* mel -> sample-rate conditioning (reference models.py:105-136) */
 #define PWV_UPSAMPLE_REPEAT 0            /* 1x1 conv + relu, every frame repeated hop times (default)       */
@@ -79,10 +80,13 @@ typedef void* pwv_stream;             /* a cudaStream_t / CUstream (0 = legacy d
 /* POD mirror of the hparams the path reads (reference hparams/default.yaml:11-33). */
 typedef struct pwv_hparams {
   int32_t n_iaf;                  /* model.n_iaf                                              */
-  int32_t filter_width;           /* model.filter_width; only 2 is implemented                 */
+  /* Shapes: the fused kernels (all three precisions) cover filter_width 2, R = D in {64,128,256}, S = 2R -- the
+   * reference's defaults and BASELINE's channel sweep. Any other positive values (free parameters in the reference,
+   * modules.py:210-244) run an un-fused general chain that needs PWV_PREC_FP32. */
+  int32_t filter_width;           /* model.filter_width (1 .. PWV_MAX_FILTER_WIDTH)            */
   int32_t residual_channels;      /* model.residual_channels (R)                               */
-  int32_t dilation_channels;      /* model.dilation_channels (D); must equal R                 */
-  int32_t skip_channels;          /* model.skip_channels (S); must equal 2*R                   */
+  int32_t dilation_channels;      /* model.dilation_channels (D)                               */
+  int32_t skip_channels;          /* model.skip_channels (S)                                   */
   int32_t condition_channels;     /* model.condition_channels (Cc)                             */
   int32_t n_mels;                 /* signal.n_mels                                             */
   int32_t hop_length;             /* signal.hop_length                                         */

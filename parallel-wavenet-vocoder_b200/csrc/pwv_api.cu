@@ -21,6 +21,7 @@
 #include "pwv_tc3.cuh"
 #include "pwv_mel.cuh"
 #include "pwv_norm.cuh"
+#include "pwv_gen.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -80,7 +81,9 @@ struct BodyOff {
 
 struct pwv_model {
   pwv_hparams hp;
-  int C, S, Cc;
+  int C, S, Cc;                  // C = residual_channels
+  int D = 0, taps = 2;           // dilation_channels, filter_width
+  bool general = false;          // shapes outside the fused kernels' coverage: the un-fused fp32 chain of pwv_gen.cuh
   int total_layers;              // sum over flows
   int max_layers;                // max over flows
   std::vector<VarSpec> vars;
@@ -245,6 +248,7 @@ static int configure_simt_kernels() {
   return PWV_OK;
 }
 static int configure_kernels(const pwv_model* m) {
+  if (m->general) return PWV_OK;      // k_gen_* use static shared memory only
   int rc = m->C == 64 ? configure_simt_kernels<64>() : m->C == 128 ? configure_simt_kernels<128>() : configure_simt_kernels<256>();
   if (rc) return rc;
   if (m->hp.precision != PWV_PREC_FP32) {
@@ -301,13 +305,18 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (!hp || !out) return fail(PWV_EINVAL, "null argument");
   *out = nullptr;
   if (hp->n_iaf < 1 || hp->n_iaf > PWV_MAX_FLOWS) return fail(PWV_EINVAL, "n_iaf=%d out of range [1,%d]", hp->n_iaf, PWV_MAX_FLOWS);
-  if (hp->filter_width != 2) return fail(PWV_EINVAL, "filter_width=%d: only 2 is implemented", hp->filter_width);
-  if (hp->residual_channels != hp->dilation_channels)
-    return fail(PWV_EINVAL, "residual_channels (%d) must equal dilation_channels (%d)", hp->residual_channels, hp->dilation_channels);
-  if (hp->skip_channels != 2 * hp->residual_channels)
-    return fail(PWV_EINVAL, "skip_channels (%d) must equal 2*residual_channels (%d)", hp->skip_channels, 2 * hp->residual_channels);
+  if (hp->filter_width < 1 || hp->filter_width > PWV_MAX_FILTER_WIDTH)
+    return fail(PWV_EINVAL, "filter_width=%d out of range [1,%d]", hp->filter_width, PWV_MAX_FILTER_WIDTH);
+  if (hp->residual_channels < 1 || hp->dilation_channels < 1 || hp->skip_channels < 1)
+    return fail(PWV_EINVAL, "residual/dilation/skip channels (%d/%d/%d) must be positive", hp->residual_channels, hp->dilation_channels, hp->skip_channels);
   const int C = hp->residual_channels;
-  if (C != 64 && C != 128 && C != 256) return fail(PWV_EINVAL, "residual_channels=%d: supported 64, 128, 256", C);
+  // The fused kernels cover R = D in {64, 128, 256}, S = 2R, filter_width 2 (the reference's defaults and BASELINE's
+  // sweep); any other shape (reference modules.py:210-244 takes them as free parameters) runs the general fp32 chain.
+  const bool general = hp->filter_width != 2 || C != hp->dilation_channels || hp->skip_channels != 2 * C || (C != 64 && C != 128 && C != 256);
+  if (general && hp->precision != PWV_PREC_FP32)
+    return fail(PWV_EINVAL, "filter_width=%d, residual/dilation/skip channels %d/%d/%d run on the general fp32 path only (precision fp32); "
+                "the tensor-core kernels cover filter_width 2, R = D in {64,128,256}, S = 2R",
+                hp->filter_width, C, hp->dilation_channels, hp->skip_channels);
   if (hp->condition_channels < 1 || hp->n_mels < 1 || hp->hop_length < 1)
     return fail(PWV_EINVAL, "bad condition_channels/n_mels/hop_length (%d/%d/%d)", hp->condition_channels, hp->n_mels, hp->hop_length);
   if (hp->cond_upsample != PWV_UPSAMPLE_REPEAT && hp->cond_upsample != PWV_UPSAMPLE_TRANSPOSED_CONV && hp->cond_upsample != PWV_UPSAMPLE_NONE)
@@ -344,6 +353,9 @@ int pwv_model_create(const pwv_hparams* hp, pwv_model** out) {
   if (!m) return fail(PWV_ENOMEM, "out of host memory");
   m->hp = *hp;
   m->C = C;
+  m->D = hp->dilation_channels;
+  m->taps = hp->filter_width;
+  m->general = general;
   m->S = hp->skip_channels;
   m->Cc = hp->condition_channels;
   m->total_layers = total;
@@ -402,6 +414,7 @@ int pwv_model_finalize(pwv_model* m) {
     if (!m->loaded[i]) return fail(PWV_ESTATE, "variable '%s' was not loaded", m->vars[i].name.c_str());
   const pwv_hparams& hp = m->hp;
   const int C = m->C, S = m->S, Cc = m->Cc;
+  const int R = m->C, D = m->D, FW = m->taps;      // (R = D = C, FW = 2 on the fused paths)
   std::vector<float> arena;
   auto put = [&](size_t n) {   // 16-float (64 B) aligned blocks
     size_t off = (arena.size() + 15) / 16 * 16;
@@ -458,14 +471,14 @@ int pwv_model_finalize(pwv_model* m) {
   m->off_wgc.assign(hp.n_iaf, 0);
   m->off_bfg.assign(hp.n_iaf, 0);
   for (int i = 0; i < hp.n_iaf; ++i) {
-    m->off_wgc[i] = put((size_t)2 * hp.n_layers[i] * Cc * 2 * C);
-    m->off_bfg[i] = put((size_t)2 * hp.n_layers[i] * 2 * C);
+    m->off_wgc[i] = put((size_t)2 * hp.n_layers[i] * Cc * 2 * D);
+    m->off_bfg[i] = put((size_t)2 * hp.n_layers[i] * 2 * D);
     for (int b = 0; b < 2; ++b) {
       BodyOff& bo = m->bodies[i * 2 + b];
       std::string p = "iaf_vocoder/iaf" + std::to_string(i) + "/" + kBodies[b];
-      bo.causal = put(2 * C);
+      bo.causal = put((size_t)FW * R);
       {
-        const auto& w = var(m, p + "/causal_layer/filter");   // [2][1][C]
+        const auto& w = var(m, p + "/causal_layer/filter");   // [FW][1][R]
         std::copy(w.begin(), w.end(), arena.begin() + bo.causal);
       }
       if (nrm_w) bo.n_causal = put_norm(p + "/causal_layer/normalize", C);
@@ -474,44 +487,44 @@ int pwv_model_finalize(pwv_model* m) {
         LayerOff& lo = bo.layers[j];
         std::string q = p + "/dilated_stack/layer" + std::to_string(j);
         if (nrm_w) {
-          lo.n_fg.gamma = put(2 * C);          // [filter | gate] halves side by side, like the pre-activation rows
-          lo.n_fg.beta = put(2 * C);
+          lo.n_fg.gamma = put(2 * D);          // [filter | gate] halves side by side, like the pre-activation rows
+          lo.n_fg.beta = put(2 * D);
           const char* part[2] = {"/normalize_filter", "/normalize_gate"};
           for (int h2 = 0; h2 < 2; ++h2) {
             const auto& g = var(m, q + part[h2] + "/gamma");
             const auto& bt = var(m, q + part[h2] + "/beta");
-            std::copy(g.begin(), g.end(), arena.begin() + lo.n_fg.gamma + h2 * C);
-            std::copy(bt.begin(), bt.end(), arena.begin() + lo.n_fg.beta + h2 * C);
+            std::copy(g.begin(), g.end(), arena.begin() + lo.n_fg.gamma + h2 * D);
+            std::copy(bt.begin(), bt.end(), arena.begin() + lo.n_fg.beta + h2 * D);
           }
           lo.n_skip = put_norm(q + "/normalize_skip_output", S);
           lo.n_dense = put_norm(q + "/normalize_dense_output", C);
         }
-        const auto& wf = var(m, q + "/filter");      // [2][C][C]
+        const auto& wf = var(m, q + "/filter");      // [FW][R][D]
         const auto& wg = var(m, q + "/gate");
-        lo.wfg = put((size_t)2 * C * 2 * C);
-        for (int tap = 0; tap < 2; ++tap)
-          for (int ci = 0; ci < C; ++ci)
-            for (int co = 0; co < C; ++co) {
-              size_t row = (size_t)tap * C + ci;   // tap 0 multiplies x[t-d], tap 1 x[t]
-              arena[lo.wfg + row * 2 * C + co] = wf[((size_t)tap * C + ci) * C + co];
-              arena[lo.wfg + row * 2 * C + C + co] = wg[((size_t)tap * C + ci) * C + co];
+        lo.wfg = put((size_t)FW * R * 2 * D);
+        for (int tap = 0; tap < FW; ++tap)
+          for (int ci = 0; ci < R; ++ci)
+            for (int co = 0; co < D; ++co) {
+              size_t row = (size_t)tap * R + ci;   // tap k multiplies x[t - (FW-1-k) d]: FW = 2: tap 0 x[t-d], tap 1 x[t]
+              arena[lo.wfg + row * 2 * D + co] = wf[((size_t)tap * R + ci) * D + co];
+              arena[lo.wfg + row * 2 * D + D + co] = wg[((size_t)tap * R + ci) * D + co];
             }
         // (unconditional graph: the conditioning projections stay zero, so the per-frame conditioning rows the
         //  kernels add are just the filter / gate biases)
-        const size_t wgc = m->off_wgc[i] + ((size_t)b * hp.n_layers[i] + j) * Cc * 2 * C;
-        const size_t bfg = m->off_bfg[i] + ((size_t)b * hp.n_layers[i] + j) * 2 * C;
+        const size_t wgc = m->off_wgc[i] + ((size_t)b * hp.n_layers[i] + j) * Cc * 2 * D;
+        const size_t bfg = m->off_bfg[i] + ((size_t)b * hp.n_layers[i] + j) * 2 * D;
         if (conditioned) {
-          const auto& gf = var(m, q + "/gc_filter");   // [1][Cc][C]
+          const auto& gf = var(m, q + "/gc_filter");   // [1][Cc][D]
           const auto& gg = var(m, q + "/gc_gate");
           for (int c = 0; c < Cc; ++c)
-            for (int co = 0; co < C; ++co) {
-              arena[wgc + (size_t)c * 2 * C + co] = gf[(size_t)c * C + co];
-              arena[wgc + (size_t)c * 2 * C + C + co] = gg[(size_t)c * C + co];
+            for (int co = 0; co < D; ++co) {
+              arena[wgc + (size_t)c * 2 * D + co] = gf[(size_t)c * D + co];
+              arena[wgc + (size_t)c * 2 * D + D + co] = gg[(size_t)c * D + co];
             }
         }
-        lo.wd = put((size_t)C * C);
-        lo.bd = put(C);
-        lo.ws = put((size_t)C * S);
+        lo.wd = put((size_t)D * R);
+        lo.bd = put(R);
+        lo.ws = put((size_t)D * S);
         lo.bs = put(S);
         {
           const auto& w = var(m, q + "/dense");
@@ -523,7 +536,7 @@ int pwv_model_finalize(pwv_model* m) {
           const auto& bf = var(m, q + "/filter_bias");
           const auto& bg = var(m, q + "/gate_bias");
           std::copy(bf.begin(), bf.end(), arena.begin() + bfg);
-          std::copy(bg.begin(), bg.end(), arena.begin() + bfg + C);
+          std::copy(bg.begin(), bg.end(), arena.begin() + bfg + D);
           const auto& bd = var(m, q + "/dense_bias");
           std::copy(bd.begin(), bd.end(), arena.begin() + lo.bd);
           const auto& bs = var(m, q + "/skip_bias");
@@ -649,7 +662,7 @@ static int cond_rows(const pwv_model* m, int T) { return cond_full_rate(m) ? T :
 static int cond_hop(const pwv_model* m) { return cond_full_rate(m) ? 1 : m->hp.hop_length; }
 
 static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
-  const int C = m->C, t_mel = 1 + T / m->hp.hop_length;
+  const int C = m->C, D = m->D, t_mel = 1 + T / m->hp.hop_length;      // (D = C on the fused paths)
   const bool tconv = m->hp.cond_upsample == PWV_UPSAMPLE_TRANSPOSED_CONV;
   const size_t crows = (size_t)cond_rows(m, T);               // conditioning rows per utterance
   size_t off = 0;
@@ -659,7 +672,7 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
     return p;
   };
   w->cproj = (float*)take(sizeof(float) * (size_t)N * crows * m->Cc);
-  w->cbias = (float*)take(sizeof(float) * (size_t)2 * m->max_layers * N * crows * 2 * C);
+  w->cbias = (float*)take(sizeof(float) * (size_t)2 * m->max_layers * N * crows * 2 * D);
   w->up[0] = w->up[1] = nullptr;
   if (tconv) {      // ping/pong stage outputs; the last stage has N * t_mel * hop rows
     size_t rows = (size_t)N * t_mel, big[2] = {0, 0};
@@ -679,13 +692,13 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
   w->x[1] = (float*)take(sizeof(float) * (size_t)N * T);
   w->zbuf = w->skip = w->fg = w->hbuf = w->total = nullptr;
   w->stats = nullptr;
-  if (m->hp.normalize_wavenet == PWV_NORM_IN) {
+  if (m->hp.normalize_wavenet == PWV_NORM_IN || m->general) {           // the un-fused chains keep every stage of a layer
     const size_t S = (size_t)m->S;
-    w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
+    w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * D);
     w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
-    w->fg = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
+    w->fg = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * D);
     w->hbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
-    if (m->hp.use_skip_connection) w->total = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
+    if (m->hp.use_skip_connection && m->hp.normalize_wavenet == PWV_NORM_IN) w->total = (float*)take(sizeof(float) * (size_t)2 * N * T * S);
   } else if (m->hp.use_skip_connection) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);
     w->skip = (float*)take(sizeof(float) * (size_t)2 * N * T * 2 * C);
@@ -693,7 +706,8 @@ static void carve(const pwv_model* m, int N, int T, char* base, Workspace* w) {
     w->zbuf = (float*)take(sizeof(float) * (size_t)2 * N * T * C);     // z planes between the gate and the dense pass (k_wide_h)
   }
   if (m->hp.normalize || m->hp.normalize_cond || m->hp.normalize_wavenet) {
-    size_t widest = (size_t)2 * N * (2 * C > m->S ? 2 * C : m->S);
+    size_t widest = (size_t)2 * N * (2 * D > m->S ? 2 * D : m->S);
+    if ((size_t)2 * N * C > widest) widest = (size_t)2 * N * C;
     if ((size_t)N * m->Cc > widest) widest = (size_t)N * m->Cc;
     w->stats = (float2*)take(sizeof(float2) * widest);
   }
@@ -852,6 +866,133 @@ static int launch_layers_in(pwv_model* m, const Workspace& w, int flow, int N, i
     dim3 g(1, (unsigned)((rows + 63) / 64), 1);
     pwv::k_row_gemm<false><<<g, 256, 0, st>>>(w.hbuf + (size_t)b * rows * S, rb, (int)rows, S, 1);
     ++*launches;
+  }
+  *cur_buf = cur;
+  PWV_CUDA(cudaGetLastError());
+  return PWV_OK;
+}
+
+// The general-shape chain (pwv_gen.cuh): any R / D / S / filter_width, with or without the 'in' normalisers and the
+// skip sum; one GEMM launch per stage covers both bodies. Reference modules.py:129-259, stage by stage.
+static void gen_gemm(const pwv::GenGemm& g, cudaStream_t st, int* launches) {
+  const dim3 grid((g.Nc + 63) / 64, (g.M + 63) / 64, 2);
+  pwv::k_gen_gemm<<<grid, 256, 0, st>>>(g);
+  ++*launches;
+}
+static int launch_layers_gen(pwv_model* m, const Workspace& w, int flow, int N, int T, cudaStream_t st, const pwv_taps* taps,
+                             int* cur_buf, int* launches) {
+  const pwv_hparams& hp = m->hp;
+  const int L = hp.n_layers[flow], crows = cond_rows(m, T), c_hop = cond_hop(m);
+  const int R = m->C, D = m->D, S = m->S, FW = m->taps;
+  const size_t rows = (size_t)N * T;
+  const bool nrm = hp.normalize_wavenet == PWV_NORM_IN;
+  const BodyOff& b0 = m->bodies[flow * 2 + 0];
+  const BodyOff& b1 = m->bodies[flow * 2 + 1];
+  int cur = *cur_buf, rc;
+  pwv::GenGemm base;
+  memset(&base, 0, sizeof(base));
+  base.lda = 1; base.taps = 1; base.dilation = 1; base.T = T; base.crows = crows; base.hop = c_hop; base.M = (int)rows;
+  if (nrm) {
+    rc = launch_in_norm(m, w, w.act[cur], 2 * N, T, R, b0.n_causal, b1.n_causal, N, false, st, launches);    // modules.py:181-182
+    if (rc) return rc;
+  }
+  for (int j = 0; j < L; ++j) {
+    const bool last = j == L - 1;
+    const LayerOff* lo[2] = {&b0.layers[j], &b1.layers[j]};
+    PWV_PROF_MARK(m, st);
+    {   // [filter | gate] pre-activations: causal convs over the FW taps + conditioning + biases (modules.py:210-228)
+      pwv::GenGemm g = base;
+      for (int b = 0; b < 2; ++b) {
+        g.A[b] = w.act[cur] + (size_t)b * rows * R;
+        g.B[b] = m->d_arena + lo[b]->wfg;
+        g.cond[b] = w.cbias + ((size_t)b * L + j) * N * crows * 2 * D;      // (carries filter_bias | gate_bias)
+        g.out[b] = w.fg + (size_t)b * rows * 2 * D;
+      }
+      g.lda = R; g.taps = FW; g.dilation = hp.dilations[flow][j]; g.K = FW * R; g.Nc = 2 * D;
+      gen_gemm(g, st, launches);
+    }
+    if (nrm) {
+      rc = launch_in_norm(m, w, w.fg, 2 * N, T, 2 * D, lo[0]->n_fg, lo[1]->n_fg, N, false, st, launches);       // modules.py:230-234
+      if (rc) return rc;
+    }
+    {
+      const size_t n = 2 * rows * D;
+      pwv::k_gen_gate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.fg, w.zbuf, D, n);                         // modules.py:236
+      ++*launches;
+    }
+    {   // dense 1x1 + bias + residual (modules.py:239-251)
+      pwv::GenGemm g = base;
+      for (int b = 0; b < 2; ++b) {
+        g.A[b] = w.zbuf + (size_t)b * rows * D;
+        g.B[b] = m->d_arena + lo[b]->wd;
+        g.bias[b] = m->d_arena + lo[b]->bd;
+        g.resid[b] = w.act[cur] + (size_t)b * rows * R;
+        g.out[b] = w.act[cur ^ 1] + (size_t)b * rows * R;
+      }
+      g.lda = D; g.K = D; g.Nc = R;
+      gen_gemm(g, st, launches);
+    }
+    cur ^= 1;
+    if (nrm) {
+      rc = launch_in_norm(m, w, w.act[cur], 2 * N, T, R, lo[0]->n_dense, lo[1]->n_dense, N, false, st, launches);   // modules.py:256-257
+      if (rc) return rc;
+    }
+    if (hp.use_skip_connection || last) {       // skip_output: summed over the layers, or the last one alone (modules.py:147,243-255)
+      pwv::GenGemm g = base;
+      for (int b = 0; b < 2; ++b) {
+        g.A[b] = w.zbuf + (size_t)b * rows * D;
+        g.B[b] = m->d_arena + lo[b]->ws;
+        g.bias[b] = m->d_arena + lo[b]->bs;
+        g.out[b] = w.skip + (size_t)b * rows * S;
+      }
+      g.lda = D; g.K = D; g.Nc = S;
+      g.accumulate = (!nrm && hp.use_skip_connection && j > 0) ? 1 : 0;
+      gen_gemm(g, st, launches);
+      if (nrm) {
+        rc = launch_in_norm(m, w, w.skip, 2 * N, T, S, lo[0]->n_skip, lo[1]->n_skip, N, false, st, launches);
+        if (rc) return rc;
+        if (hp.use_skip_connection) {
+          const size_t n = 2 * rows * S;
+          if (j == 0) PWV_CUDA(cudaMemcpyAsync(w.total, w.skip, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+          else { pwv::k_add_inplace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.total, w.skip, n); ++*launches; }
+        }
+      }
+    }
+    PWV_PROF_MARK(m, st);
+    if (m->profiling) ++m->prof_launches;
+    if (taps && taps->layer_out && taps->layer_flow == flow && taps->layer_index == j && (taps->layer_body == 0 || taps->layer_body == 1))
+      PWV_CUDA(cudaMemcpyAsync(taps->layer_out, w.act[cur] + (size_t)taps->layer_body * rows * R, sizeof(float) * rows * R, cudaMemcpyDeviceToDevice, st));
+  }
+  // post-net: relu -> [norm] -> 1x1 + bias -> relu -> [norm] -> 1x1 + bias (modules.py:148-165)
+  float* src = (nrm && hp.use_skip_connection) ? w.total : w.skip;
+  if (nrm) {
+    rc = launch_in_norm(m, w, src, 2 * N, T, S, b0.n_pp1, b1.n_pp1, N, true, st, launches);      // (applies the relu first)
+    if (rc) return rc;
+  }
+  {
+    pwv::GenGemm g = base;
+    const BodyOff* bo[2] = {&b0, &b1};
+    for (int b = 0; b < 2; ++b) {
+      g.A[b] = src + (size_t)b * rows * S;
+      g.B[b] = m->d_arena + bo[b]->w1;
+      g.bias[b] = m->d_arena + bo[b]->b1;
+      g.out[b] = w.hbuf + (size_t)b * rows * S;
+    }
+    g.lda = S; g.K = S; g.Nc = S; g.relu_in = nrm ? 0 : 1; g.relu_out = 1;
+    gen_gemm(g, st, launches);
+    if (nrm) {
+      rc = launch_in_norm(m, w, w.hbuf, 2 * N, T, S, b0.n_pp2, b1.n_pp2, N, false, st, launches);
+      if (rc) return rc;
+    }
+    pwv::GenGemm h = base;
+    for (int b = 0; b < 2; ++b) {
+      h.A[b] = w.hbuf + (size_t)b * rows * S;
+      h.B[b] = m->d_arena + bo[b]->w2;
+      h.bias[b] = m->d_arena + bo[b]->b2;
+      h.out[b] = w.ss + (size_t)b * rows;
+    }
+    h.lda = S; h.K = S; h.Nc = 1;
+    gen_gemm(h, st, launches);
   }
   *cur_buf = cur;
   PWV_CUDA(cudaGetLastError());
@@ -1433,14 +1574,16 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
   int cur = 0, xcur = 0;
   const float* x_prev = noise;
   const bool nrm_f = hp.normalize == PWV_NORM_IN;     // x is combined and normalised explicitly after every flow
-  if (hp.normalize_wavenet == PWV_NORM_IN && ((size_t)N * T + 63) / 64 > 65535)
-    return fail(PWV_EINVAL, "normalize_wavenet: N*T = %zu exceeds the un-fused post-net's grid (4,194,240 samples per call)", (size_t)N * T);
+  if ((hp.normalize_wavenet == PWV_NORM_IN || m->general) && ((size_t)N * T + 63) / 64 > 65535)
+    return fail(PWV_EINVAL, "%s: N*T = %zu exceeds the un-fused chain's grid (4,194,240 samples per call)",
+                m->general ? "general-shape path" : "normalize_wavenet", (size_t)N * T);
   for (int i = 0; i < hp.n_iaf; ++i) {
     const int L = hp.n_layers[i];
     // per-layer conditioning terms of this flow: cbias[b][j] = cproj . [gc_filter|gc_gate] + [bf|bg]
     {
-      pwv::RowGemmBatch rb{m->d_arena + m->off_wgc[i], (size_t)Cc * 2 * C, m->d_arena + m->off_bfg[i], (size_t)2 * C,
-                           w.cbias, (size_t)N * crows * 2 * C,
+      const int D = m->D;      // (= C on the fused paths)
+      pwv::RowGemmBatch rb{m->d_arena + m->off_wgc[i], (size_t)Cc * 2 * D, m->d_arena + m->off_bfg[i], (size_t)2 * D,
+                           w.cbias, (size_t)N * crows * 2 * D,
                            hp.precision == PWV_PREC_FP32 ? nullptr : m->d_arena + m->off_colscale};
       const int M = N * crows;
       if (hp.precision != PWV_PREC_FP32 && m->tc.d_cond) {
@@ -1458,17 +1601,32 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
         dim3 grid(m_tiles, zsplit);
         if (hp.precision == PWV_PREC_BF16) pwv::k_cbias_tc<true, false><<<grid, pwv::TCC_THREADS, pwv::tcc_smem_bytes(Cc), st>>>(q);
         else pwv::k_cbias_tc<false, true><<<grid, pwv::TCC_THREADS, pwv::tcc_smem_bytes(Cc), st>>>(q);
-      } else if (Cc % 16 == 0 && Cc <= 2 * C) {
+      } else if (!m->general && Cc % 16 == 0 && Cc <= 2 * C) {
         rc = launch_cond_gemm(C, w.cproj, rb, M, Cc, 2 * L, st);
         if (rc) return rc;
       } else {
-        dim3 grid((2 * C + 63) / 64, (M + 63) / 64, 2 * L);
-        pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * C);
+        dim3 grid((2 * D + 63) / 64, (M + 63) / 64, 2 * L);
+        pwv::k_row_gemm<false><<<grid, 256, 0, st>>>(w.cproj, rb, M, Cc, 2 * D);
       }
       ++launches;
     }
     // front: IAF combine of the previous flow + causal layers
-    if (wide) {
+    if (m->general) {
+      pwv::GenFront f;
+      f.x_prev = x_prev;
+      f.scale = (i == 0 || nrm_f) ? nullptr : w.ss;
+      f.shift = (i == 0 || nrm_f) ? nullptr : w.ss + (size_t)N * T;
+      f.x_new = w.x[xcur];
+      f.wc[0] = m->d_arena + m->bodies[i * 2 + 0].causal;
+      f.wc[1] = m->d_arena + m->bodies[i * 2 + 1].causal;
+      f.act = w.act[cur];
+      f.N = N; f.T = T; f.R = C; f.taps = m->taps;
+      const size_t total = (size_t)N * T * C;
+      pwv::k_gen_front<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(f);
+      ++launches;
+      x_prev = w.x[xcur];
+      xcur ^= 1;
+    } else if (wide) {
       pwv::FrontWParams f;
       f.x_prev = x_prev;
       f.scale = i == 0 ? nullptr : w.ss;
@@ -1516,7 +1674,9 @@ int pwv_forward(pwv_model* m, const float* noise, const float* mel, float* wav, 
       x_prev = w.x[xcur];
       xcur ^= 1;
     }
-    if (hp.normalize_wavenet == PWV_NORM_IN) {
+    if (m->general) {
+      rc = launch_layers_gen(m, w, i, N, T, st, taps, &cur, &launches);
+    } else if (hp.normalize_wavenet == PWV_NORM_IN) {
       if (C == 64) rc = launch_layers_in<64>(m, w, i, N, T, st, taps, &cur, &launches);
       else if (C == 128) rc = launch_layers_in<128>(m, w, i, N, T, st, taps, &cur, &launches);
       else rc = launch_layers_in<256>(m, w, i, N, T, st, taps, &cur, &launches);

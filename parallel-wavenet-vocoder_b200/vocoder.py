@@ -39,8 +39,8 @@ def _assert_supported(hp):
 def tensor_core_covers(dims):
     """Graphs the tcgen05 kernels implement: R = D = 64, S = 128 (csrc/pwv_tc2.cuh: the whole layer in one kernel) and
     R = D in {128, 256}, S = 2R without skip connections (csrc/pwv_tc3.cuh: streamed-K gate and dense passes)."""
-    if dims['R'] != dims['D'] or dims['S'] != 2 * dims['R']:
-        return False
+    if dims['R'] != dims['D'] or dims['S'] != 2 * dims['R'] or dims['k'] != 2:
+        return False                # free parameters in the reference (modules.py:210-244): the general fp32 chain (csrc/pwv_gen.cuh)
     if dims.get('norm_flow') or dims.get('norm_cond') or dims.get('norm_wavenet'):
         return False                # a statistic over the whole time axis sits between the stages: un-fused fp32 kernels
     return dims['R'] == 64 or (dims['R'] in (128, 256) and not dims['use_skip'])
@@ -53,7 +53,7 @@ def resolve_precision(dims, precision):
         if tensor_core_covers(dims):
             return 'f16x3'
         import warnings
-        warnings.warn(f"engine.precision 'auto': residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} "
+        warnings.warn(f"engine.precision 'auto': filter_width {dims['k']}, residual/dilation/skip channels {dims['R']}/{dims['D']}/{dims['S']} "
                       f"(use_skip_connection={bool(dims['use_skip'])}, normalisers {dims.get('norm_flow')!r}/{dims.get('norm_cond')!r}/"
                       f"{dims.get('norm_wavenet')!r}) are outside the tensor-core kernels' coverage; "
                       f"running the exact fp32 FFMA kernels", RuntimeWarning, stacklevel=2)

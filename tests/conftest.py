@@ -61,6 +61,9 @@ def load_golden(hp, name):
     dil = [[int(v) for v in row[:n]] for row, n in zip(g['dilations'], n_layers)]
     model = {'n_iaf': int(g['n_iaf']), 'dilations': dil}
     model['use_skip_connection'] = (name == 'ref_skip.npz')     # generated with model.use_skip_connection=True (modules.py:147)
+    for key in ('filter_width', 'residual_channels', 'dilation_channels', 'skip_channels', 'use_skip_connection'):
+        if key in g.files:              # the free shape parameters (ref_shapes.npz)
+            model[key] = bool(g[key]) if key == 'use_skip_connection' else int(g[key])
     if 'cond_upsample_method' in g.files:
         model['cond_upsample_method'] = str(g['cond_upsample_method'])
     if 'normalize' in g.files:          # every normaliser call site (reference modules.py:263-284)

@@ -9,7 +9,7 @@ in the reference's Python. What they do not pin: TensorFlow's kernels (restated 
 
     python tests/golden/make_golden_from_reference.py
 
-writes tests/golden/ref_norm.npz / ref_norm_tran.npz (all normalisers 'in'), tests/golden/ref_tran.npz (cond_upsample_method 'transposed_conv'), tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
+writes tests/golden/ref_shapes.npz (filter_width 3, R/D/S = 24/40/56, skip sum), tests/golden/ref_norm.npz / ref_norm_tran.npz (all normalisers 'in'), tests/golden/ref_tran.npz (cond_upsample_method 'transposed_conv'), tests/golden/ref_small.npz (default hparams, N=2, T=1600, fp64 arithmetic on float32-valued
 inputs and weights, non-zero biases), tests/golden/ref_flows.npz (a 2-flow graph with per-flow
 outputs) and tests/golden/ref_varlist.txt (the graph's variable names in creation order).
 """
@@ -183,6 +183,27 @@ def main():
     d['cond_upsample_method'] = np.array('none')
     np.savez_compressed(os.path.join(HERE, 'ref_nocond.npz'), **d)
     ref_hp.model.cond_upsample_method = 'repeat'
+
+    # ---- fixture 8: the free shape parameters (reference modules.py:210-244, hparams/default.yaml:22-26): filter_width 3,
+    #      residual / dilation / skip channels all different and none a multiple of 16, skip sum on
+    shapes = {'filter_width': 3, 'residual_channels': 24, 'dilation_channels': 40, 'skip_channels': 56, 'use_skip_connection': True}
+    for key, value in shapes.items():
+        setattr(ref_hp.model, key, value)
+    my_hp.set_hparam_dict({'model': dict(shapes, n_iaf=2, dilations=dil)}, case='golden/shapes')
+    weights = W.init_weights(my_hp, seed=49, bias_std=0.1, dtype=np.float32)
+    wav, created = run_reference(tf, ref_models, weights, noise, mel)
+    assert created == list(W.variable_shapes(my_hp).keys()), 'variable list / creation order differs (free shapes)'
+    assert weights['iaf_vocoder/iaf0/scalar/dilated_stack/layer0/filter'].shape == (3, 24, 40)
+    ours = O.iaf_vocoder_forward(noise, mel, weights, dil, hop, use_skip_connection=True, dtype=np.float64)
+    err = np.abs(ours - wav).max()
+    print('free-shape graph: reference code (under shim) vs oracle: max|delta| = %.3e, |wav|max = %.3f' % (err, np.abs(wav).max()))
+    assert err < 1e-12
+    d = pack(noise, mel, wav, weights, dil, (49, 0.1, 1.0))
+    for key, value in shapes.items():
+        d[key] = np.int64(value)
+    np.savez_compressed(os.path.join(HERE, 'ref_shapes.npz'), **d)
+    ref_hp.model.filter_width, ref_hp.model.residual_channels, ref_hp.model.dilation_channels = 2, 64, 64
+    ref_hp.model.skip_channels, ref_hp.model.use_skip_connection = 128, False
     print('wrote ref_small.npz, ref_flows.npz, ref_varlist.txt (%d variables in the default graph)' % len(W.variable_shapes(my_hp.set_hparam_yaml('default'))))
 
 

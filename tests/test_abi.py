@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(L.EXPORTS) == declared
-    assert lib.pwv_version() == 200
+    assert lib.pwv_version() == 201
 
 
 def test_hparams_struct_matches_header():
@@ -60,7 +60,15 @@ def test_model_create_validates(hp):
     assert names == list(pkg('weights').variable_shapes(hp).keys())
     lib.pwv_model_destroy(h)
 
-    hp.model.filter_width = 3
+    hp.model.filter_width = 3                           # any shape on the general fp32 chain, none of it on tensor cores
+    _, h3, rc = _create(hp)
+    assert rc == 0
+    lib.pwv_model_variable(h3, 1, ctypes.byref(name), shape, ctypes.byref(ndim))
+    assert name.value.endswith(b'causal_layer/filter') and list(shape)[:3] == [3, 1, 64]
+    lib.pwv_model_destroy(h3)
+    _, _, rc = _create(hp, 'f16x3')
+    assert rc == -1 and b'general fp32 path' in lib.pwv_last_error()
+    hp.model.filter_width = 0
     _, _, rc = _create(hp)
     assert rc == -1 and b'filter_width' in lib.pwv_last_error()
     hp.model.filter_width = 2
@@ -71,9 +79,15 @@ def test_model_create_validates(hp):
         assert lib.pwv_debug_set(h2, b'path', 0) == 0 and lib.pwv_debug_set(h2, b'no_such_switch', 1) == -1
         lib.pwv_model_destroy(h2)
     hp.model.use_skip_connection = False
-    hp.model.residual_channels = 48
-    _, _, rc = _create(hp)
+    hp.model.residual_channels = 48                     # R != D, S != 2R: general chain; bf16 / f16x3 refuse
+    _, h4, rc = _create(hp)
+    assert rc == 0
+    lib.pwv_model_destroy(h4)
+    _, _, rc = _create(hp, 'bf16')
     assert rc == -1
+    hp.model.residual_channels = 0
+    _, _, rc = _create(hp)
+    assert rc == -1 and b'positive' in lib.pwv_last_error()
     with pytest.raises(ValueError):
         L.make_hparams(pkg('weights').model_dims(hp), 'fp16')
 

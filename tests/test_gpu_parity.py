@@ -130,7 +130,7 @@ def test_edge_shapes(hp, n, t, precision):
 
 
 @pytest.mark.parametrize('name,precision', [(n, p) for n in ('ref_small.npz', 'ref_flows.npz', 'ref_tran.npz', 'ref_skip.npz', 'ref_nocond.npz')
-                                            for p in ('fp32', 'f16x3')] + [('ref_norm.npz', 'fp32'), ('ref_norm_tran.npz', 'fp32')])
+                                            for p in ('fp32', 'f16x3')] + [('ref_norm.npz', 'fp32'), ('ref_norm_tran.npz', 'fp32'), ('ref_shapes.npz', 'fp32')])
 def test_golden_fixture(hp, name, precision):
     """Committed fixtures produced by executing the reference's own modules.py/models.py under the
     numpy TF stand-in (tests/golden/make_golden_from_reference.py): pinned to the reference's graph code, not to
@@ -302,6 +302,54 @@ def test_instance_normalisers(hp, which):
     assert err <= TOL * max(1.0, float(np.abs(ref).max()))
     solo = model.forward(torch.from_numpy(noise[1:2]).cuda(), torch.from_numpy(mel[1:2]).cuda())
     assert torch.equal(solo[0], out[1])
+
+
+@pytest.mark.parametrize('shape', [
+    dict(filter_width=3, residual_channels=24, dilation_channels=40, skip_channels=56),
+    dict(filter_width=2, residual_channels=64, dilation_channels=32, skip_channels=128),          # only R != D
+    dict(filter_width=2, residual_channels=64, dilation_channels=64, skip_channels=64),           # only S != 2R
+    dict(filter_width=3, residual_channels=64, dilation_channels=64, skip_channels=128),          # only the filter width
+    dict(filter_width=1, residual_channels=17, dilation_channels=5, skip_channels=3),             # degenerate: no past tap at all
+    dict(filter_width=4, residual_channels=96, dilation_channels=80, skip_channels=72, use_skip_connection=True),
+    dict(filter_width=3, residual_channels=24, dilation_channels=40, skip_channels=56, use_skip_connection=True,
+         normalize='in', normalize_cond='in', normalize_wavenet='in'),
+    dict(filter_width=3, residual_channels=24, dilation_channels=40, skip_channels=56, normalize_wavenet='in'),
+    dict(filter_width=3, residual_channels=24, dilation_channels=40, skip_channels=56, cond_upsample_method='transposed_conv'),
+    dict(filter_width=2, residual_channels=48, dilation_channels=48, skip_channels=96, cond_upsample_method='none'),
+], ids=lambda d: '-'.join(str(v) for v in d.values()))
+def test_free_shape_parameters(hp, shape):
+    """filter_width, residual / dilation / skip channels are free parameters of the reference (modules.py:210-244,
+    hparams/default.yaml:22-26). Outside the fused kernels' coverage the un-fused general chain (csrc/pwv_gen.cuh) runs,
+    with every other graph option on top: against the float64 oracle incl. the layer / scale-shift / flow taps, bit-exact
+    batch independence and determinism; tensor-core precisions refuse these shapes."""
+    small_case(hp, dilations=((1, 2, 4, 512), (3, 1, 8)), n=3, t=800, precision='fp32')
+    for key, value in shape.items():
+        setattr(hp.model, key, value)
+    weights = pkg('weights').init_weights(hp, seed=23, bias_std=0.2)
+    noise, mel = O.synthetic_inputs(3, 800, 80, 80, mel_seed=5, noise_seed=6)
+    taps = {}
+    ref = _oracle(hp, weights, noise, mel, taps)
+    (out, cap), model = _run(hp, weights, noise, mel, taps={'flow_out': True, 'scale_shift': True, 'layer': (1, 0, 1)})
+    want_layer = taps['iaf_vocoder/iaf1/scalar/dilated_stack/layer1']
+    assert cap['layer_out'].shape == want_layer.shape == (3, 800, shape['residual_channels'])
+    assert np.abs(cap['layer_out'].cpu().numpy() - want_layer).max() <= TOL * max(1.0, float(np.abs(want_layer).max()))
+    ss = cap['scale_shift'].cpu().numpy()
+    for i in range(2):
+        for b, body in enumerate(('scalar', 'shifter')):
+            want = taps[f'iaf_vocoder/iaf{i}/{body}']
+            assert np.abs(ss[i, b] - want).max() <= TOL * max(1.0, float(np.abs(want).max())), (i, body)
+        want = taps[f'iaf_vocoder/iaf{i}']
+        assert np.abs(cap['flow_out'][i].cpu().numpy() - want).max() <= TOL * max(1.0, float(np.abs(want).max())), i
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(shape, 'max|delta| =', err, 'max|ref| =', np.abs(ref).max())
+    assert err <= TOL * max(1.0, float(np.abs(ref).max()))
+    dn, dm = torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda()
+    assert torch.equal(model.forward(dn, dm), out)
+    assert torch.equal(model.forward(dn[2:3], dm[2:3])[0], out[2])
+    with pytest.raises(RuntimeError, match='general fp32 path'):
+        _run(hp, weights, noise, mel, precision='f16x3')
+    with pytest.warns(RuntimeWarning, match='outside the tensor-core'):
+        assert pkg('vocoder').resolve_precision(pkg('weights').model_dims(hp), 'auto') == 'fp32'
 
 
 @pytest.mark.parametrize('channels', [64, 128])

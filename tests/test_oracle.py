@@ -9,10 +9,10 @@ from conftest import ROOT, load_golden, pkg, small_case
 from oracle import iaf_oracle as O
 
 
-@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz', 'ref_norm.npz', 'ref_norm_tran.npz', 'ref_nocond.npz'])
+@pytest.mark.parametrize('name', ['ref_small.npz', 'ref_flows.npz', 'ref_skip.npz', 'ref_tran.npz', 'ref_norm.npz', 'ref_norm_tran.npz', 'ref_nocond.npz', 'ref_shapes.npz'])
 def test_oracle_reproduces_reference_golden(hp, name):
     weights, noise, mel, wav, dil = load_golden(hp, name)
-    skip = name == 'ref_skip.npz'        # generated with model.use_skip_connection=True
+    skip = bool(hp.model.use_skip_connection)        # ref_skip / ref_shapes were generated with model.use_skip_connection=True
     if name == 'ref_small.npz':          # keep the CPU suite quick: 1 of the 2 utterances
         noise, mel, wav = noise[:1], mel[:1], wav[:1]
     got = O.iaf_vocoder_forward(noise, mel, weights, dil, 80, use_skip_connection=skip, dtype=np.float64)
