@@ -68,6 +68,7 @@ struct ThLayerParams {
   // slots' GEMMs interleave and the slots fall into lock-step, the effect DESIGN 4.1 describes for round 1):
   int use_cp;               // 1: the MMA issuer moves the landed boxes into TMEM itself (tcgen05.cp) instead of the workers
   int split1;               // 1: GEMM1 starts on the x[t-d] half of K as soon as those columns are copied (the x[t] boxes land later)
+  int double_a;             // bf16: A operand double-buffered by tile parity, next tile copied while GEMM2 runs (default 1)
   int split2;               // 1: GEMM2 starts on the first 16-channel chunk of each half of z while the gate computes the second
   long long* trace;
 };
@@ -168,11 +169,16 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       const uint64_t dW2lo = smem_desc_kmajor_noswizzle(smem_u32(smem + TC_OFF_W2LO), 1024, 128);
       constexpr uint32_t ID1 = idesc_f16(128, 128, BF16), ID2 = idesc_f16(128, 64, BF16);
       const uint32_t tD = tmem + s * 256;
-      const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+      const uint32_t tAlo = tD + 192;
+      // bf16 has one operand plane, so columns [192, 256) of the slot are free: the A operand is double-buffered by tile
+      // parity there, and the workers copy tile j+1 while GEMM2 of tile j runs (see the worker loop)
+      const bool db = BF16 && !p.use_cp && p.double_a;
+      const bool split1 = p.split1 && !db;
+      auto tA_of = [&](int j) { return tD + 128 + (db ? (uint32_t)(j & 1) * 64 : 0u); };
       const int tiles_s = (n_local + 1 - s) / 2;
       // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi over K steps [k0, k1) (a step = 16 channels = 8 TMEM columns of A and two
       // 16-byte K-chunks of B); D2 likewise over the listed steps of z.
-      auto gemm1_part = [&](int k0, int k1, uint32_t acc) {
+      auto gemm1_part = [&](uint32_t tAhi, int k0, int k1, uint32_t acc) {
         if (SPLIT) {
 #pragma unroll 1
           for (int ks = k0; ks < k1; ++ks, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
@@ -182,7 +188,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
 #pragma unroll 1
         for (int ks = k0; ks < k1; ++ks, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
       };
-      auto gemm2_part = [&](int k0, int kstep, uint32_t acc) {      // steps k0, k0 + kstep, ... < 4
+      auto gemm2_part = [&](uint32_t tAhi, int k0, int kstep, uint32_t acc) {      // steps k0, k0 + kstep, ... < 4
         if (SPLIT) {
 #pragma unroll 1
           for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
@@ -195,6 +201,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       const uint32_t box0 = smem_u32(smem + TH_SMEM_STAGE0 + s * TH_STAGE_BYTES);
       for (int j = 0; j < tiles_s; ++j) {
         const uint32_t par = j & 1;
+        const uint32_t tAhi = tA_of(j);
         if (p.use_cp) {
           // the landed boxes go into the slot's A columns by tcgen05.cp, in order with the MMAs that read them
           if (j > 0) mbar_wait(&bars->a_free[s], (j - 1) & 1);      // the workers have read D2 and x of the slot's previous tile
@@ -211,27 +218,27 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
               for (int k = 0; k < 4; ++k)
                 tmem_cp_128x256b((q ? tAlo : tAhi) + b * 32 + k * 8, smem_desc_kmajor_sw128(box0 + (2 * b + q) * TH_BOX_BYTES + k * 32));
           mma_commit(&bars->boxes_free[s]);
-          gemm1_part(0, 8, 0);
+          gemm1_part(tAhi, 0, 8, 0);
           mma_commit(&bars->d1_ready[s]);
           tc_unlock<SPLIT>(&bars->mma_lock);
           TC_TRACE(2, j, s * 8 + 1);
         } else {
         mbar_wait(&bars->ax_ready[s], par);
-        if (p.split1) {                    // the x[t-d] half of K (columns copied first) ...
+        if (split1) {                      // the x[t-d] half of K (columns copied first) ...
           tc_lock<SPLIT>(&bars->mma_lock);
           tc_fence_after_sync();
           TC_TRACE(2, j, s * 8 + 0);
-          gemm1_part(0, 4, 0);
+          gemm1_part(tAhi, 0, 4, 0);
           tc_unlock<SPLIT>(&bars->mma_lock);
         }
         mbar_wait(&bars->ay_ready[s], par);
         tc_lock<SPLIT>(&bars->mma_lock);
         tc_fence_after_sync();
-        if (p.split1) {                    // ... then the x[t] half
-          gemm1_part(4, 8, 1);
+        if (split1) {                      // ... then the x[t] half
+          gemm1_part(tAhi, 4, 8, 1);
         } else {
           TC_TRACE(2, j, s * 8 + 0);
-          gemm1_part(0, 8, 0);
+          gemm1_part(tAhi, 0, 8, 0);
         }
         mma_commit(&bars->d1_ready[s]);
         tc_unlock<SPLIT>(&bars->mma_lock);
@@ -244,17 +251,17 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
           tc_lock<SPLIT>(&bars->mma_lock);
           tc_fence_after_sync();
           TC_TRACE(2, j, s * 8 + 2);
-          gemm2_part(0, 2, 0);
+          gemm2_part(tAhi, 0, 2, 0);
           tc_unlock<SPLIT>(&bars->mma_lock);
         }
         mbar_wait(&bars->zb_ready[s], par);
         tc_lock<SPLIT>(&bars->mma_lock);
         tc_fence_after_sync();
         if (p.split2) {
-          gemm2_part(1, 2, 1);
+          gemm2_part(tAhi, 1, 2, 1);
         } else {
           TC_TRACE(2, j, s * 8 + 2);
-          gemm2_part(0, 1, 0);
+          gemm2_part(tAhi, 0, 1, 0);
         }
         mma_commit(&bars->d2_ready[s]);
         tc_unlock<SPLIT>(&bars->mma_lock);
@@ -386,7 +393,10 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const uint32_t tD = tmem + slot * 256 + lane_base;
-    const uint32_t tAhi = tD + 128, tAlo = tD + 192;
+    const uint32_t tAlo = tD + 192;
+    const bool db = BF16 && !p.use_cp && p.double_a;          // bf16: A operand double-buffered by tile parity (columns [192, 256) are free)
+    const bool split1 = p.split1 && !db;
+    auto tA_of = [&](int j) { return tD + 128 + (db ? (uint32_t)(j & 1) * 64 : 0u); };
     uint8_t* stage = smem + TH_SMEM_STAGE0 + slot * TH_STAGE_BYTES;
     const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + half * 32;
     const float* scal = reinterpret_cast<const float*>(smem + TC_OFF_SCAL);
@@ -398,7 +408,9 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       if (lane == 0) mbar_arrive(bar);
     };
     // boxes -> the slot's A columns, verbatim: K = channel (x[t-d]) / 64 + channel (x[t]), two 16-bit elements per column
-    auto a_copy = [&](uint32_t par) {
+    // `hand_over` false: the columns are written but the tile is not announced yet (a_copy_announce does that later)
+    auto a_copy = [&](int jn, bool hand_over) {
+      const uint32_t par = jn & 1, tAhi = tA_of(jn);
       uint32_t v[16];
       mbar_wait(&bars->x_full[slot], par);
 #pragma unroll
@@ -406,7 +418,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         th_ld_row64(stage + q * TH_BOX_BYTES, r, half * 4, v);
         tmem_st16((q ? tAlo : tAhi) + half * 16, v);
       }
-      if (p.split1) {                           // the x[t-d] half of K is handed over on its own: GEMM1 may start on it
+      if (split1) {                             // the x[t-d] half of K is handed over on its own: GEMM1 may start on it
         tmem_wait_st();
         tc_fence_before_sync();
         warp_arrive(&bars->ax_ready[slot]);
@@ -418,17 +430,28 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         tmem_st16((q ? tAlo : tAhi) + 32 + half * 16, v);
       }
       tmem_wait_st();
+      if (!hand_over) return;
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (!p.split1) mbar_arrive(&bars->ax_ready[slot]);
+        if (!split1) mbar_arrive(&bars->ax_ready[slot]);
+        mbar_arrive(&bars->ay_ready[slot]);
+      }
+    };
+    // One arrival says two things to the MMA issuer: the next tile's operand is in its A columns, and this warp has read
+    // its part of the accumulator the next GEMM1 overwrites.
+    auto a_copy_announce = [&]() {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->ax_ready[slot]);
         mbar_arrive(&bars->ay_ready[slot]);
       }
     };
 
     if (n_s > 0) {
       if (tracer) TC_TRACE(slot, 0, 0);
-      if (!p.use_cp) a_copy(0);
+      if (!p.use_cp) a_copy(0, true);
       if (tracer) TC_TRACE(slot, 0, 4);
       mbar_wait(&bars->w_ready, 0);
     }
@@ -439,6 +462,7 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       const int tile = cta_in_body + (slot + 2 * j) * ctas_per_body;
       const int n = tile / p.tiles_per_utt, t_first = (tile % p.tiles_per_utt) * TC_TM, t = t_first + r;
       const uint32_t par = j & 1;
+      const uint32_t tAhi = tA_of(j);
       const int frame = (min(t, p.T - 1) + p.hop / 2) / p.hop;
       const float4* cb;
       if (p.cb_in_smem) {               // staged with the tile's x[t-d] boxes: row (frame - first frame of the tile)
@@ -501,8 +525,12 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
           }
         }
       }
+      // bf16 (double-buffered A): the next tile's boxes go into the other A buffer NOW, while GEMM2 of this tile runs; the
+      // copy leaves the slot's critical chain (gate -> GEMM2 -> read-out -> GEMM1 of the next tile)
+      const bool early = !LAST && db && j + 1 < n_s;
       if constexpr (!LAST) {
         if (tracer) TC_TRACE(slot, j, 6);
+        if (early) a_copy(j + 1, false);
         // ---- D2 and x[t] (hi, lo) of my 32 channels -> registers; after this the slot's TMEM belongs to the next tile
         mbar_wait_sleepy(&bars->d2_ready[slot], par);
         tc_fence_after_sync();
@@ -519,8 +547,10 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         warp_arrive(&bars->a_free[slot]);            // my part of D2 / x is in registers: the slot's TMEM may take the next tile
         if (j + 1 < n_s) mbar_wait(&bars->boxes_free[slot], (j + 1) & 1);   // ... whose boxes must have left before they become the staging
         else if (j >= 1) mbar_wait(&bars->y_full[slot], (j + 1) & 1);
+      } else if (early) {
+        a_copy_announce();
       } else if (j + 1 < n_s) {
-        a_copy((j + 1) & 1);
+        a_copy(j + 1, true);
       } else {
         tc_fence_before_sync();
         if (j >= 1) mbar_wait(&bars->y_full[slot], (j + 1) & 1);   // the store of tile j-1 has read the staging boxes

@@ -1,0 +1,41 @@
+#!/bin/bash
+# Round 2, GPU call K: bf16 with the A operand double-buffered in TMEM (early copy) against the single-buffered order
+mkdir -p gpurun_out
+timeout -k 5 90 python - > gpurun_out/k_tiny.log 2>&1 <<'PY'
+import importlib, numpy as np, torch
+P = 'parallel-wavenet-vocoder_b200'
+hp = importlib.import_module(P + '.hparam').hparam; W = importlib.import_module(P + '.weights'); V = importlib.import_module(P + '.vocoder'); IO = importlib.import_module(P + '.io')
+hp.set_hparam_dict({'model': {'n_iaf': 2, 'dilations': [[1, 2, 4, 512], [1, 8]]}, 'generate': {'batch_size': 3, 'length': 4000}}, case='t')
+d = W.model_dims(hp); w = W.init_weights(hp, seed=1, bias_std=0.1)
+for n, t in ((3, 4000), (1, 320), (8, 16000)):
+    nz, ml = IO.synthetic_batch(n, t, 80, 80)
+    a = V.PwvModel(d, w, 'bf16').forward(torch.from_numpy(nz).cuda(), torch.from_numpy(ml).cuda())
+    b = V.PwvModel(d, w, 'bf16', debug={'double_a': 0}).forward(torch.from_numpy(nz).cuda(), torch.from_numpy(ml).cuda())
+    torch.cuda.synchronize(); print(n, t, 'double_a == single:', torch.equal(a, b), float((a - b).abs().max()), flush=True)
+PY
+OK=$?; echo "tiny rc=$OK"; tail -4 gpurun_out/k_tiny.log
+[ $OK -eq 0 ] || exit 1
+timeout -k 5 400 python -m pytest tests/test_gpu_parity.py -x -q -k "bf16 or switches" > gpurun_out/k_t1.log 2>&1; echo "t1 rc=$?"
+tail -4 gpurun_out/k_t1.log
+run() {  # name, extra args...
+  name=$1; shift
+  timeout -k 5 100 python bench.py --steps 10 --no-cpu-baseline --no-e2e --sustain-s 1 "$@" > gpurun_out/k_bench_$name.json 2> gpurun_out/k_bench_$name.err
+  rc=$?; echo "bench $name rc=$rc"
+  python - "$name" <<'PY'
+import json, sys
+try:
+    d = json.load(open('gpurun_out/k_bench_%s.json' % sys.argv[1]))
+    r = d['roofline']
+    print('   ms/step %.3f  us/layer %.2f  frac %.3f  iso_us %.2f  sustained ms %.3f @ %s MHz  clocks %s' % (d['ms_per_step'], r['us_per_layer'], r['frac'], r['isolated_launch_us'], d['sustained']['ms_per_step'], d['sustained']['clocks'].get('sm_mhz'), d['clocks']['sm_mhz']))
+except Exception as e:
+    print('   no line:', e)
+PY
+  return $rc
+}
+run bf16_c2_db --precision bf16 || exit 1
+run bf16_c2_single --precision bf16 --debug double_a=0
+run bf16_c2_db2 --precision bf16
+run bf16_c3_db --precision bf16 --workload c3 --steps 5
+run bf16_c3_single --precision bf16 --workload c3 --steps 5 --debug double_a=0
+run f16x3_c2
+timeout -k 5 60 python tools/tc_trace.py bf16 2 > gpurun_out/k_trace_bf16_l2.txt 2>&1; echo "trace rc=$?"
