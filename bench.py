@@ -396,7 +396,7 @@ def main():
         clocks = sampler.stop(t_begin, t_end)           # samples of the K timed steps
         if sustained is not None:
             sustained['clocks'] = window_clocks(sampler.lines, t_sus0, t_sus1)
-            launches += launches_per_forward * sustained['iterations']
+            sustained['gpu_launches'] = launches_per_forward * sustained['iterations']     # (`gpu_launches` of the line: the K timed steps only)
 
     # ---- roofline of the dominant kernel (gated dilated layer), separate profiled steps
     pk = peaks()
