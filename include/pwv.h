@@ -165,7 +165,7 @@ int pwv_debug_set_trace(pwv_model* m, long long* device_buffer, int layer_index)
 int pwv_profile_read(pwv_model* m, double* layer_ms, int* layer_launches, double* forward_ms);
 /* Debug / A-B switches for tests and measurement tools (the library never reads the environment): key one of
  * "path" (1 = 16-bit activation planes, the default; 0 = the round-1 fp32-row kernels), "pdl", "tile_flags", "flow",
- * "seg", "rotate", "stagger", "variant", "trace_flow", "split1", "split2", "cp", "double_a" -- see csrc/pwv_api.cu. Unknown keys fail with PWV_EINVAL. */
+ * "seg", "rotate", "stagger", "variant", "trace_flow", "split1", "split2", "cp", "double_a", "z_in_d" -- see csrc/pwv_api.cu. Unknown keys fail with PWV_EINVAL. */
 int pwv_debug_set(pwv_model* m, const char* key, int value);
 
 /* ---- mel front end: the step immediately upstream of the path.

@@ -131,6 +131,7 @@ struct pwv_model {
   bool trace_flow = false;       // "trace_flow" (path 0): the phase trace follows k_flow_tc instead of forcing per-layer launches
   bool use_cp = false;           // "cp" (path 1): boxes -> TMEM by tcgen05.cp from the MMA issuer instead of the workers' ld.shared + tcgen05.st
   bool split1 = false;           // "split1" (path 1): GEMM1 starts on the x[t-d] half of K before the x[t] boxes are copied
+  bool z_in_d = true;            // "z_in_d" (path 1, f16x3): gate output into the dead gate-accumulator columns, next tile copied while GEMM2 runs
   bool double_a = true;          // "double_a" (path 1, bf16): A operand double-buffered in TMEM, next tile copied while GEMM2 of this one runs
   bool split2 = false;           // "split2" (path 1): GEMM2 starts on the first half of the z chunks
   int trace_launch = -1;         // index of the gated layer to trace (0 .. total layers - 1, flows concatenated)
@@ -1309,6 +1310,7 @@ static int launch_layers_h(pwv_model* m, const Workspace& w, const CUtensorMap* 
     p.split1 = m->split1 ? 1 : 0;
     p.split2 = m->split2 ? 1 : 0;
     p.double_a = m->double_a ? 1 : 0;
+    p.z_in_d = m->z_in_d ? 1 : 0;
     p.z_out = (hp.use_skip_connection && !last) ? w.zbuf : nullptr;
     p.trace = (m->trace && m->trace_launch == (int)(layer_base / 2) + j) ? m->trace : nullptr;
     if (m->profiling == 1 || (m->profiling == 2 && j == 0)) PWV_PROF_MARK(m, st);
@@ -1783,6 +1785,7 @@ int pwv_debug_set(pwv_model* m, const char* key, int value) {
   else if (k == "split1") m->split1 = value != 0;
   else if (k == "split2") m->split2 = value != 0;
   else if (k == "double_a") m->double_a = value != 0;
+  else if (k == "z_in_d") m->z_in_d = value != 0;
   else return fail(PWV_EINVAL, "unknown debug switch '%s'", key);
   return PWV_OK;
 }

@@ -68,6 +68,8 @@ struct ThLayerParams {
   // slots' GEMMs interleave and the slots fall into lock-step, the effect DESIGN 4.1 describes for round 1):
   int use_cp;               // 1: the MMA issuer moves the landed boxes into TMEM itself (tcgen05.cp) instead of the workers
   int split1;               // 1: GEMM1 starts on the x[t-d] half of K as soon as those columns are copied (the x[t] boxes land later)
+  int z_in_d;               // f16x3: the gate output goes into the dead gate-accumulator columns instead of the x[t-d] operand
+                            //   columns, so the A columns are free right after GEMM1 and the next tile is copied while GEMM2 runs (default 1)
   int double_a;             // bf16: A operand double-buffered by tile parity, next tile copied while GEMM2 runs (default 1)
   int split2;               // 1: GEMM2 starts on the first 16-channel chunk of each half of z while the gate computes the second
   long long* trace;
@@ -173,7 +175,11 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       // bf16 has one operand plane, so columns [192, 256) of the slot are free: the A operand is double-buffered by tile
       // parity there, and the workers copy tile j+1 while GEMM2 of tile j runs (see the worker loop)
       const bool db = BF16 && !p.use_cp && p.double_a;
-      const bool split1 = p.split1 && !db;
+      // f16x3 has no free columns, but the gate accumulators [64, 128) are dead once a worker has read them: z (hi + lo,
+      // 16 columns per 16-channel chunk) goes THERE, D2 into [0, 64), and the A columns belong to the next tile as soon as
+      // GEMM1 is through and the workers have taken x[t] into registers
+      const bool zd = !BF16 && !p.use_cp && p.z_in_d;
+      const bool split1 = p.split1 && !db && !zd;
       auto tA_of = [&](int j) { return tD + 128 + (db ? (uint32_t)(j & 1) * 64 : 0u); };
       const int tiles_s = (n_local + 1 - s) / 2;
       // D1 = A1lo.W1hi + A1hi.W1lo + A1hi.W1hi over K steps [k0, k1) (a step = 16 channels = 8 TMEM columns of A and two
@@ -189,14 +195,16 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
         for (int ks = k0; ks < k1; ++ks, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW1hi + (uint64_t)(ks * 256), ID1, acc);
       };
       auto gemm2_part = [&](uint32_t tAhi, int k0, int kstep, uint32_t acc) {      // steps k0, k0 + kstep, ... < 4
+        // z of step ks: columns ks * 8 of the hi / lo operand planes, or (zd) hi at 64 + ks * 16, lo 8 columns further
+        const uint32_t zhi = zd ? tD + 64 : tAhi, zlo = zd ? tD + 72 : tAlo, zstep = zd ? 16 : 8;
         if (SPLIT) {
 #pragma unroll 1
-          for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAlo + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
+          for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, zlo + ks * zstep, dW2hi + (uint64_t)(ks * 128), ID2, acc);
 #pragma unroll 1
-          for (int ks = k0; ks < 4; ks += kstep) mma_f16_ts(tD, tAhi + ks * 8, dW2lo + (uint64_t)(ks * 128), ID2, 1);
+          for (int ks = k0; ks < 4; ks += kstep) mma_f16_ts(tD, zhi + ks * zstep, dW2lo + (uint64_t)(ks * 128), ID2, 1);
         }
 #pragma unroll 1
-        for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, tAhi + ks * 8, dW2hi + (uint64_t)(ks * 128), ID2, acc);
+        for (int ks = k0; ks < 4; ks += kstep, acc = 1) mma_f16_ts(tD, zhi + ks * zstep, dW2hi + (uint64_t)(ks * 128), ID2, acc);
       };
       const uint32_t box0 = smem_u32(smem + TH_SMEM_STAGE0 + s * TH_STAGE_BYTES);
       for (int j = 0; j < tiles_s; ++j) {
@@ -395,7 +403,8 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
     const uint32_t tD = tmem + slot * 256 + lane_base;
     const uint32_t tAlo = tD + 192;
     const bool db = BF16 && !p.use_cp && p.double_a;          // bf16: A operand double-buffered by tile parity (columns [192, 256) are free)
-    const bool split1 = p.split1 && !db;
+    const bool zd = !BF16 && !p.use_cp && p.z_in_d;           // f16x3: z into the dead gate-accumulator columns (see the MMA issuer)
+    const bool split1 = p.split1 && !db && !zd;
     auto tA_of = [&](int j) { return tD + 128 + (db ? (uint32_t)(j & 1) * 64 : 0u); };
     uint8_t* stage = smem + TH_SMEM_STAGE0 + slot * TH_STAGE_BYTES;
     const float* bd_s = reinterpret_cast<const float*>(smem + TC_OFF_BD) + half * 32;
@@ -506,8 +515,10 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
             for (int e = 0; e < 8; ++e) { v0[e] = z[e]; v1[e] = z[8 + e]; }
             split8x<BF16, SPLIT, PK>(v0, hi, lo);
             split8x<BF16, SPLIT, PK>(v1, hi + 4, lo + 4);
-            tmem_st8(tAhi + half * 16 + c * 8, hi);
-            if (SPLIT) tmem_st8(tAlo + half * 16 + c * 8, lo);
+            // (zd: chunk c of my half lands on the 16 gate-accumulator columns I have just consumed -- g0r / g1r)
+            const uint32_t zc = tD + 64 + half * 32 + c * 16;
+            tmem_st8(zd ? zc : tAhi + half * 16 + c * 8, hi);
+            if (SPLIT) tmem_st8(zd ? zc + 8 : tAlo + half * 16 + c * 8, lo);
             if (c == 1 || p.split2) {          // (without the GEMM2 split both halves are handed over together)
               tmem_wait_st();
               tc_fence_before_sync();
@@ -527,17 +538,26 @@ k_layer_h(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CU
       }
       // bf16 (double-buffered A): the next tile's boxes go into the other A buffer NOW, while GEMM2 of this tile runs; the
       // copy leaves the slot's critical chain (gate -> GEMM2 -> read-out -> GEMM1 of the next tile)
-      const bool early = !LAST && db && j + 1 < n_s;
+      // f16x3 (zd): GEMM1 is through and z sits in the accumulator columns, so once x[t] of this tile is in registers the
+      // A columns are free and take the next tile at the same point.
+      const bool early = !LAST && (db || zd) && j + 1 < n_s;
       if constexpr (!LAST) {
         if (tracer) TC_TRACE(slot, j, 6);
+        if (zd) {
+          tmem_ld16(tAhi + 32 + half * 16, xh);
+          if (SPLIT) tmem_ld16(tAlo + 32 + half * 16, xl);
+          tmem_wait_ld();
+        }
         if (early) a_copy(j + 1, false);
         // ---- D2 and x[t] (hi, lo) of my 32 channels -> registers; after this the slot's TMEM belongs to the next tile
         mbar_wait_sleepy(&bars->d2_ready[slot], par);
         tc_fence_after_sync();
         if (tracer) TC_TRACE(slot, j, 7);
         tmem_ld32(tD + half * 32, dr);
-        tmem_ld16(tAhi + 32 + half * 16, xh);
-        if (SPLIT) tmem_ld16(tAlo + 32 + half * 16, xl);
+        if (!zd) {
+          tmem_ld16(tAhi + 32 + half * 16, xh);
+          if (SPLIT) tmem_ld16(tAlo + 32 + half * 16, xl);
+        }
         tmem_wait_ld();
       }
       if (tracer) TC_TRACE(slot, j, 9);

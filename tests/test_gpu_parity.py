@@ -433,7 +433,7 @@ def test_layer_kernel_variants_bit_identical(hp, path, variant, precision):
 
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize('precision', ['f16x3', 'bf16'])
-@pytest.mark.parametrize('switches', [{'cp': 1}, {'split1': 1, 'split2': 1}, {'tile_flags': 0}, {'pdl': 0}, {'double_a': 0}])
+@pytest.mark.parametrize('switches', [{'cp': 1}, {'split1': 1, 'split2': 1}, {'tile_flags': 0}, {'pdl': 0}, {'double_a': 0}, {'z_in_d': 0}])
 def test_layer_h_switches_bit_identical(hp, precision, switches):
     """k_layer_h's A/B switches change WHO moves operands and WHEN the MMAs are issued, never the arithmetic: boxes into
     TMEM by tcgen05.cp from the MMA issuer ('cp'), K-split GEMMs, no tile flags, no programmatic dependent launch --
