@@ -90,6 +90,7 @@ class PwvModel:
                                                       shp, arr.ndim))
         _lib.check(self.lib.pwv_model_finalize(self._h))
         self._ws = None
+        self.max_workspace_bytes = None     # None: bounded by the device's free memory (see _utterances_per_pass)
 
     def close(self):
         h = getattr(self, '_h', None)
@@ -111,8 +112,44 @@ class PwvModel:
     def _workspace(self, n, t, device):
         need = self.workspace_bytes(n, t)
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = None                       # (free the old block before asking for the larger one)
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws
+
+    def _workspace_limit(self, device):
+        """Bytes a workspace may take: `max_workspace_bytes` if set, else 90 % of what the device could give now
+        (free memory + the workspace this model already holds)."""
+        if self.max_workspace_bytes:
+            return int(self.max_workspace_bytes)
+        free, _ = torch.cuda.mem_get_info(device)
+        held = self._ws.numel() if self._ws is not None and self._ws.device == device else 0
+        return int(0.9 * (free + held))
+
+    def _utterances_per_pass(self, n, t, device):
+        """How many utterances one pwv_forward call may take. The path is independent per utterance (bit for bit:
+        tests/test_gpu_parity.py), so a batch whose workspace would not fit -- a full-rate conditioning
+        ('transposed_conv', normalize_cond) materialises 2 x layers x N x T x 2D floats -- is run in several passes."""
+        def need(k):
+            try:
+                return self.workspace_bytes(k, t)
+            except _lib.PwvError as e:
+                if e.code != -4:              # PWV_ENOMEM: larger than the whole device
+                    raise
+                return float('inf')
+        if self._ws is not None and self._ws.device == device and need(n) <= self._ws.numel():
+            return n
+        limit = self._workspace_limit(device)
+        if need(n) <= limit:
+            return n
+        one = need(1)
+        if one > limit:
+            raise MemoryError(f'one utterance of {t} samples needs a {one}-byte workspace, {limit} are available')
+        k = max(1, min(n, int(limit // one)))       # (a lower estimate: the fixed part is counted once per utterance)
+        while k > 1 and need(k) > limit:
+            k -= 1
+        while k < n and need(k + 1) <= limit:
+            k += 1
+        return k
 
     def forward(self, noise, mel, out=None, taps=None):
         """noise (N,T) f32 cuda, mel (N,1+T//hop,n_mels) f32 cuda -> wav (N,T) f32 cuda.
@@ -125,6 +162,11 @@ class PwvModel:
         assert mel.shape == (n, 1 + t // self.dims['hop'], self.dims['n_mels']), mel.shape
         if out is None:
             out = torch.empty((n, t), dtype=torch.float32, device=noise.device)
+        k = n if taps else self._utterances_per_pass(n, t, noise.device)
+        if k < n:
+            for i in range(0, n, k):
+                self.forward(noise[i:i + k], mel[i:i + k], out=out[i:i + k])
+            return out
         ws = self._workspace(n, t, noise.device)
         tp = None
         captured = {}

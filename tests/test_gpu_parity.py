@@ -352,6 +352,29 @@ def test_free_shape_parameters(hp, shape):
         assert pkg('vocoder').resolve_precision(pkg('weights').model_dims(hp), 'auto') == 'fp32'
 
 
+@pytest.mark.parametrize('precision,method', [('f16x3', 'repeat'), ('fp32', 'transposed_conv')])
+def test_oversized_batch_runs_in_several_passes(hp, precision, method):
+    """A batch whose workspace does not fit (full-rate conditioning materialises 2 x layers x N x T x 2D floats: a
+    c3-sized 'transposed_conv' batch would need 189 GB) is split over utterances by the host side; the result is the
+    unsplit one bit for bit, and a single utterance that cannot fit is a MemoryError, not a CUDA failure."""
+    small_case(hp, dilations=((1, 2, 4, 512), (1, 8)), n=5, t=1600, precision=precision)
+    hp.model.cond_upsample_method = method
+    weights = pkg('weights').init_weights(hp, seed=29, bias_std=0.1)
+    noise, mel = O.synthetic_inputs(5, 1600, 80, 80)
+    whole, model = _run(hp, weights, noise, mel, precision=precision)
+    model.max_workspace_bytes = model.workspace_bytes(2, 1600)
+    assert model._utterances_per_pass(5, 1600, whole.device) == 5          # the workspace it already holds is enough
+    model._ws = None
+    assert model._utterances_per_pass(5, 1600, whole.device) == 2
+    split = model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
+    assert torch.equal(split, whole)
+    assert model._ws.numel() == model.workspace_bytes(2, 1600)
+    model._ws = None
+    model.max_workspace_bytes = model.workspace_bytes(1, 1600) - 1
+    with pytest.raises(MemoryError):
+        model.forward(torch.from_numpy(noise).cuda(), torch.from_numpy(mel).cuda())
+
+
 @pytest.mark.parametrize('channels', [64, 128])
 def test_use_skip_connection(hp, channels):
     """model.use_skip_connection=True (reference modules.py:147: the post-net sees the SUM of every layer's skip
