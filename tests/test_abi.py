@@ -182,3 +182,25 @@ def test_unconditional_graph_variable_list(hp):
         W.variable_shapes(hp)
     with pytest.raises(ValueError):
         pkg('vocoder')._assert_supported(hp)
+
+
+def test_batch_split_arithmetic_of_the_host_side():
+    """PwvModel._utterances_per_pass: how many utterances one pwv_forward call takes when the workspace is bounded
+    (host logic only; the GPU suite checks that the split result is bit-identical)."""
+    V, L = pkg('vocoder'), pkg('_lib')
+    m = V.PwvModel.__new__(V.PwvModel)           # no library handle: the method only asks workspace_bytes
+    m._ws, m.max_workspace_bytes = None, 1000
+    m.workspace_bytes = lambda k, t: 100 + 300 * k
+    assert m._utterances_per_pass(5, 10, 'cpu') == 3        # 100 + 900 fits exactly, 1300 does not
+    assert m._utterances_per_pass(2, 10, 'cpu') == 2
+    m.max_workspace_bytes = 399
+    with pytest.raises(MemoryError, match='one utterance'):
+        m._utterances_per_pass(5, 10, 'cpu')
+
+    def needs_more_than_the_device(k, t):        # what pwv_workspace_bytes reports past the device's size
+        if k > 2:
+            raise L.PwvError(-4, 'workspace exceeds the device')
+        return 400 * k
+    m.workspace_bytes, m.max_workspace_bytes = needs_more_than_the_device, 10_000
+    assert m._utterances_per_pass(64, 10, 'cpu') == 2
+    m.close = lambda: None
