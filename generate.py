@@ -51,6 +51,9 @@ def generate(case='default', ckpt=None, debug=False):
 
     # summaries -- reference generate.py:41-45,71-73
     io.write_audio_summaries(hp.logdir, hp.signal.sr, pred=pred_wav, gt=gt_wav)
+    if (hp.get('engine', {}) or {}).get('write_wav'):          # PCM16 files like reference audio.py:19-20 (off by default)
+        for i, w in enumerate(np.asarray(pred_wav).reshape(len(pred_wav), -1)):
+            io.write_wav(w, hp.signal.sr, os.path.join(hp.logdir, 'pred_%d.wav' % i))
     print('Done.')
     return pred_wav
 

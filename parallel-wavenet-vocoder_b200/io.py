@@ -9,6 +9,8 @@
   variable names (weights.py).
 * `write_audio_summaries`: `audio/pred`, `audio/gt` into a TensorBoard event file in `hp.logdir`
   (reference generate.py:41-45,71-73) when tensorboard is importable, plus `.npy` copies.
+* `write_wav`: PCM16 wav files (reference audio.py:19-20 `write_wav`, soundfile's 'PCM_16'); `engine.write_wav: true`
+  makes `generate.py` leave `pred_<i>.wav` beside the summaries.
 """
 import glob
 import os
@@ -108,3 +110,16 @@ def write_audio_summaries(logdir, sr, pred, gt=None):
         if gt is not None:
             writer.add_audio('audio/gt/%d' % i, torch.as_tensor(gt[i]).reshape(1, -1).clamp(-1, 1), 0, sample_rate=int(sr))
     writer.close()
+
+
+def write_wav(wav, sr, path):
+    """Mono PCM16 wav (reference audio.py:19-20: `sf.write(path, wav, sr, format='wav', subtype='PCM_16')`): float
+    samples in [-1, 1) scaled by 32768 and clipped to the int16 range, as libsndfile's default conversion does."""
+    import wave
+    data = np.asarray(wav, dtype=np.float64).reshape(-1)
+    pcm = np.clip(np.rint(data * 32768.0), -32768, 32767).astype('<i2')
+    with wave.open(path, 'wb') as fh:
+        fh.setnchannels(1)
+        fh.setsampwidth(2)
+        fh.setframerate(int(sr))
+        fh.writeframes(pcm.tobytes())

@@ -57,3 +57,21 @@ def test_generation_data_reads_wav_files(hp, tmp_path):
     gt, mel, noise = data.next_batch()
     assert gt.shape == (2, 4000, 1) and mel.shape == (2, 51, 80) and noise is None
     assert mel.dtype == np.float32 and -1.0 <= mel.min() and mel.max() <= 1.0
+
+
+def test_write_wav_pcm16_round_trip(tmp_path):
+    """io.write_wav (reference audio.py:19-20, PCM_16) -> melspec.read_wav: equal to within half an int16 step,
+    clipped at full scale, sample rate kept."""
+    import numpy as np
+    from conftest import pkg
+    io, M = pkg('io'), pkg('melspec')
+    rng = np.random.RandomState(0)
+    wav = np.concatenate([rng.uniform(-1, 1, 4000), [1.5, -1.5, 0.0, 32767.4 / 32768.0]]).astype(np.float32)
+    path = str(tmp_path / 'x.wav')
+    io.write_wav(wav, 16000, path)
+    from scipy.io import wavfile
+    sr, raw = wavfile.read(path)
+    assert sr == 16000 and raw.dtype == np.int16 and raw.shape == (4004,)
+    assert raw[4000] == 32767 and raw[4001] == -32768 and raw[4002] == 0
+    back = M.read_wav(path, 16000)
+    assert np.abs(back[:4000] - wav[:4000]).max() <= 0.5 / 32768 + 1e-7
