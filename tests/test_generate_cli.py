@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from conftest import ROOT
+from conftest import ROOT, pkg
 
 
 def _load():
@@ -40,3 +40,41 @@ def test_generate_raises_without_a_gpu(tmp_path, monkeypatch):
     with pytest.raises(Exception) as err:
         mod.generate('bench/c1')
     assert not isinstance(err.value, (ImportError, FileNotFoundError, KeyError)), repr(err.value)
+
+
+def test_generate_flow_and_sinks_with_a_stand_in_model(tmp_path, monkeypatch):
+    """Everything of generate() around the forward pass -- hparams case, synthetic dataset, 'no checkpoint' branch,
+    audio summaries, .npy, optional PCM16 wav files -- with the model object replaced by a stand-in that returns a
+    known waveform (the forward pass itself is the GPU suite's business; this is NOT a CPU implementation of it)."""
+    import numpy as np
+    import models as models_shim
+    monkeypatch.chdir(ROOT)
+    mod = _load()
+    hp = pkg('hparam').hparam
+
+    class StandIn:
+        def __init__(self, batch_size, length):
+            self.n, self.t = batch_size, length
+
+        def __call__(self, wav, melspec, is_training=False, noise=None):
+            assert wav is None and melspec.shape == (self.n, 1 + self.t // 80, 80) and noise.shape == (self.n, self.t)
+            t = np.arange(self.t, dtype=np.float32) / 16000.0
+            return torch.from_numpy(np.stack([0.5 * np.sin(2 * np.pi * 220.0 * (i + 1) * t) for i in range(self.n)])[..., None])
+
+    monkeypatch.setattr(models_shim, 'IAFVocoder', StandIn)
+    logdir = str(tmp_path / 'logdir')
+
+    def with_overrides(self, case):              # the case's hparams, redirected to a scratch logdir, wav files on
+        return self.set_hparam_dict({'logdir_path': logdir, 'data_path': 'synthetic', 'engine': {'write_wav': True},
+                                     'generate': {'batch_size': 2, 'length': 1600}}, case=case)
+    monkeypatch.setattr(type(hp), 'set_hparam_yaml', with_overrides)
+    pred = mod.generate('bench/c1')
+    assert pred.shape == (2, 1600, 1)
+    out = hp.logdir
+    assert np.array_equal(np.load(os.path.join(out, 'pred_wav.npy')), pred)
+    from scipy.io import wavfile
+    for i in range(2):
+        sr, raw = wavfile.read(os.path.join(out, 'pred_%d.wav' % i))
+        assert sr == 16000 and raw.dtype == np.int16 and len(raw) == 1600
+        assert np.abs(raw / 32768.0 - pred[i, :, 0]).max() <= 0.5 / 32768 + 1e-7
+    assert any(f.startswith('events.out.tfevents') for f in os.listdir(out))
