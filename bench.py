@@ -426,7 +426,10 @@ def main():
     layer_s = float(np.median(layer_ms)) * 1e-3                          # device time of all gated-layer launches
     achieved = n_gated * bytes_per_layer / layer_s / 1e9
     mac_per_layer = 2 * n * t * (2 * dims['R'] * 2 * dims['D'] + dims['D'] * dims['R'])
-    if precision == 'fp32':
+    general = dims['k'] != 2 or dims['R'] != dims['D'] or dims['S'] != 2 * dims['R'] or dims['R'] not in (64, 128, 256)
+    if precision == 'fp32' and general:
+        kernel, kkey = 'k_gen_gemm chain: un-fused general-shape gated layer, fp32 FFMA (csrc/pwv_gen.cuh)', 'k_gen:fp32'
+    elif precision == 'fp32':
         kernel, kkey = 'k_layer_simt: gated dilated layer, fp32 FFMA, both bodies per launch', 'k_layer_simt:fp32'
     elif planes_path:
         kernel = ('k_layer_h: gated dilated layer on tcgen05, activations as 16-bit planes in HBM, both bodies per launch; '
